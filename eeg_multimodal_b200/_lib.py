@@ -1,0 +1,81 @@
+"""ctypes binding of libpgfuse.so (the C ABI in include/pgfuse.h).
+
+This is the only place the product touches native code.  There is NO fallback: if the
+shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgfuse.so")
+
+DT_F32, DT_BF16 = 0, 1
+NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32 = range(7)
+
+P, I, LL, F, U32, U64, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint, C.c_ulonglong, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pgfuse.h one to one
+SIGNATURES = {
+    "pgf_version": (I, []),
+    "pgf_last_error": (C.c_char_p, []),
+    "pgf_num_sms": (I, []),
+    "pgf_dp_coeffs": (I, [P, F, I, I, P, P, P, P]),
+    "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, P]),
+    "pgf_perturb_gate_bwd_dp_workspace": (SZ, [I, I]),
+    "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, I, I, I, P, U64, U32, U64, P, P, SZ, P, I, P]),
+    "pgf_minmax_norm_bwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, I, LL, I, P, LL, P, LL, P, LL, P]),
+    "pgf_linear_fwd": (I, [P, LL, LL, P, LL, P, LL, P, LL, LL, I, I, I, I, I, P]),
+    "pgf_linear_bwd_dx_workspace": (SZ, [I, I, I, I]),
+    "pgf_linear_bwd_dx": (I, [P, LL, LL, P, LL, P, I, LL, LL, P, LL, LL, I, I, I, I, P, SZ, P]),
+    "pgf_linear_bwd_dw": (I, [P, LL, LL, P, LL, LL, P, LL, P, LL, I, I, I, I, I, P]),
+    "pgf_gemm_bf16": (I, [P, LL, I, P, LL, I, P, LL, I, I, I, I, P, P, LL, I, P]),
+    "pgf_cls_ce_workspace": (SZ, [I, I, I]),
+    "pgf_cls_ce": (I, [P, I, LL, LL, P, LL, P, LL, P, LL, I, I, I, F, F, I, I, P, LL, P, LL, P, P, I, LL, LL, P, LL, P, LL, P, SZ, P]),
+    "pgf_adam_step": (I, [P, P, P, P, P, LL, I, F, F, F, F, F, P]),
+    "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
+    "pgf_colsum_workspace": (SZ, [I, I]),
+    "pgf_colsum": (I, [P, I, LL, I, I, P, P, SZ, P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libpgfuse.so; raises if it has not been built (python -m eeg_multimodal_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m eeg_multimodal_b200.build` or `__graft_entry__.build()`.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+# kernels launched per successful call (for the bench's `gpu_launches` count)
+LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2}
+launch_count = 0
+launch_by_name = {}
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise on a non-zero status."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    n = LAUNCHES_PER_CALL.get(name, 1)
+    launch_count += n
+    launch_by_name[name] = launch_by_name.get(name, 0) + n
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {load().pgf_last_error().decode()}")
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))

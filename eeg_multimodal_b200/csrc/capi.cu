@@ -1,0 +1,243 @@
+// extern "C" layer of libpgfuse.so: argument validation + dispatch to the kernels.
+// Contract: include/pgfuse.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/pgfuse.h"
+#include "pgf_kernels.cuh"
+
+namespace pgf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace pgf
+
+using namespace pgf;
+
+extern "C" {
+
+int pgf_version(void) { return 100; }
+const char* pgf_last_error(void) { return g_err; }
+int pgf_num_sms(void) { return num_sms(); }
+
+int pgf_dp_coeffs(const float* DP, float exp_eps, int fixed_formula, int D, float* w, float* eps_hat, float* deps_dDP,
+                  void* stream) {
+  PGF_CHECK_ARG(DP && D > 0, "pgf_dp_coeffs: DP is NULL or D <= 0");
+  return dp_coeffs(DP, exp_eps, fixed_formula, D, w, eps_hat, deps_dDP, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
+                         int d2, long long ld2, const float* w, const float* eps_hat, int B, int noise_mode,
+                         const float* lap, const float* gum, unsigned long long seed, unsigned int offset,
+                         unsigned long long row0, float tau, int hard, int want_gate, void* out, int out_dtype,
+                         long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, void* stream) {
+  if (B == 0) return PGF_OK;  // empty batch: nothing to do
+  PGF_CHECK_ARG(B > 0, "pgf_perturb_gate_fwd: B < 0");
+  PGF_CHECK_ARG(x0 && d0 > 0, "pgf_perturb_gate_fwd: first feature block is required");
+  PGF_CHECK_ARG(d1 >= 0 && d2 >= 0 && (d1 == 0 || x1) && (d2 == 0 || x2), "pgf_perturb_gate_fwd: block pointer/size mismatch");
+  PGF_CHECK_ARG(d1 > 0 || d2 == 0, "pgf_perturb_gate_fwd: block 2 given without block 1");
+  PGF_CHECK_ARG((d0 % 4) == 0 && (d1 % 4) == 0 && (d2 % 4) == 0, "pgf_perturb_gate_fwd: block widths must be multiples of 4");
+  PGF_CHECK_ARG((ld0 % 4) == 0 && (ld1 % 4) == 0 && (ld2 % 4) == 0 && aligned16(x0) && aligned16(x1) && aligned16(x2),
+                "pgf_perturb_gate_fwd: feature blocks must be 16-byte aligned with row strides multiple of 4");
+  PGF_CHECK_ARG(out && aligned16(out) && (ld_out % 4) == 0, "pgf_perturb_gate_fwd: out must be 16-byte aligned");
+  PGF_CHECK_ARG(out_dtype == PGF_DT_F32 || out_dtype == PGF_DT_BF16, "pgf_perturb_gate_fwd: bad out_dtype");
+  PGF_CHECK_ARG(noise_mode >= 0 && noise_mode <= 2, "pgf_perturb_gate_fwd: bad noise_mode %d", noise_mode);
+  if (noise_mode != PGF_NOISE_NONE) PGF_CHECK_ARG(w && eps_hat, "pgf_perturb_gate_fwd: w / eps_hat required");
+  if (noise_mode == PGF_NOISE_INJECTED) PGF_CHECK_ARG(lap && aligned16(lap), "pgf_perturb_gate_fwd: injected mode needs lap");
+  bool gate = want_gate != 0 && noise_mode != PGF_NOISE_NONE;
+  if (noise_mode == PGF_NOISE_INJECTED && !gum) gate = false;
+  PGF_CHECK_ARG(tau > 0.f, "pgf_perturb_gate_fwd: tau must be > 0");
+  PerturbFwdArgs a;
+  a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
+  a.ld[0] = ld0; a.ld[1] = ld1; a.ld[2] = ld2;
+  a.d[0] = d0; a.d[1] = d1; a.d[2] = d2;
+  a.D = d0 + d1 + d2;
+  a.B = B;
+  a.w = w; a.eps_hat = eps_hat; a.lap = lap; a.gum = gum;
+  a.seed = seed; a.offset = offset; a.row0 = row0;
+  a.tau = tau; a.inv_tau = 1.0f / tau; a.hard = hard;
+  a.out = out; a.ld_out = ld_out; a.gate_idx = gate_idx; a.row_min = row_min; a.row_max = row_max;
+  return perturb_gate_fwd(a, noise_mode, out_dtype, gate, static_cast<cudaStream_t>(stream));
+}
+
+size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D) {
+  if (B <= 0 || D <= 0) return 0;
+  return static_cast<size_t>(perturb_bwd_slabs(B, D)) * D * sizeof(float);
+}
+
+int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, int B, int D, int noise_mode, const float* lap,
+                            unsigned long long seed, unsigned int offset, unsigned long long row0, const float* deps_dDP,
+                            float* workspace, size_t workspace_bytes, float* dDP, int accumulate, void* stream) {
+  PGF_CHECK_ARG(D > 0 && (D % 4) == 0 && dDP && deps_dDP, "pgf_perturb_gate_bwd_dp: bad D / NULL outputs");
+  if (B == 0) {
+    if (!accumulate) cudaMemsetAsync(dDP, 0, sizeof(float) * D, static_cast<cudaStream_t>(stream));
+    return PGF_OK;
+  }
+  PGF_CHECK_ARG(B > 0 && dF && aligned16(dF) && (ld % 4) == 0, "pgf_perturb_gate_bwd_dp: dF must be 16-byte aligned");
+  PGF_CHECK_ARG(noise_mode == PGF_NOISE_INJECTED || noise_mode == PGF_NOISE_PHILOX, "pgf_perturb_gate_bwd_dp: bad noise_mode");
+  if (noise_mode == PGF_NOISE_INJECTED) PGF_CHECK_ARG(lap, "pgf_perturb_gate_bwd_dp: injected mode needs lap");
+  PGF_CHECK_ARG(workspace, "pgf_perturb_gate_bwd_dp: workspace is NULL");
+  return perturb_gate_bwd_dp(dF, dF_dtype, ld, B, D, noise_mode, lap, seed, offset, row0, deps_dDP, workspace,
+                             workspace_bytes, dDP, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_minmax_norm_bwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
+                        int d2, long long ld2, const void* dn, int dn_dtype, long long ld_dn, int B, float* dx0,
+                        long long ldd0, float* dx1, long long ldd1, float* dx2, long long ldd2, void* stream) {
+  if (B == 0) return PGF_OK;
+  PGF_CHECK_ARG(B > 0 && x0 && dx0 && dn && d0 > 0, "pgf_minmax_norm_bwd: NULL argument");
+  PGF_CHECK_ARG((d1 == 0 || (x1 && dx1)) && (d2 == 0 || (x2 && dx2)), "pgf_minmax_norm_bwd: block pointer/size mismatch");
+  PGF_CHECK_ARG((d0 % 4) == 0 && (d1 % 4) == 0 && (d2 % 4) == 0, "pgf_minmax_norm_bwd: block widths must be multiples of 4");
+  NormBwdArgs a;
+  a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
+  a.ld[0] = ld0; a.ld[1] = ld1; a.ld[2] = ld2;
+  a.dx[0] = dx0; a.dx[1] = dx1; a.dx[2] = dx2;
+  a.ld_dx[0] = ldd0; a.ld_dx[1] = ldd1; a.ld_dx[2] = ldd2;
+  a.d[0] = d0; a.d[1] = d1; a.d[2] = d2;
+  a.D = d0 + d1 + d2;
+  a.B = B;
+  a.dn = dn;
+  a.ld_dn = ld_dn;
+  return minmax_norm_bwd(a, dn_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_linear_fwd(const float* X, long long ldx, long long sX, const float* W, long long sW, const float* bias,
+                   long long sb, float* Y, long long ldy, long long sY, int B, int N, int K, int act, int n_models,
+                   void* stream) {
+  if (B == 0 || n_models == 0) return PGF_OK;
+  PGF_CHECK_ARG(X && W && Y && B > 0 && N > 0 && K > 0 && n_models > 0, "pgf_linear_fwd: NULL or non-positive argument");
+  PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(X) && aligned16(W) && (sX % 4) == 0 && (sW % 4) == 0,
+                "pgf_linear_fwd: K, ldx, strides must be multiples of 4 and X, W 16-byte aligned");
+  LinFwdArgs a;
+  a.X = X; a.ldx = ldx; a.sX = sX; a.W = W; a.sW = sW; a.bias = bias; a.sb = sb; a.Y = Y; a.ldy = ldy; a.sY = sY;
+  a.B = B; a.N = N; a.K = K; a.act = act;
+  return linear_fwd(a, n_models, static_cast<cudaStream_t>(stream));
+}
+
+size_t pgf_linear_bwd_dx_workspace(int B, int N, int K, int n_models) {
+  if (B <= 0 || n_models <= 0) return 0;
+  return linear_dx_workspace(B, N, K, n_models);
+}
+
+int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float* W, long long sW, const float* mask_src,
+                      int mask_mode, long long ld_mask, long long s_mask, float* dX, long long ldx, long long sdX, int B, int N, int K,
+                      int n_models, float* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0 || n_models == 0) return PGF_OK;
+  PGF_CHECK_ARG(dY && W && dX && workspace && B > 0 && N > 0 && K > 0, "pgf_linear_bwd_dx: NULL or non-positive argument");
+  PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(W) && aligned16(dX) && (sW % 4) == 0 && (sdX % 4) == 0 &&
+                    (!mask_src || ((ld_mask % 4) == 0 && aligned16(mask_src) && (s_mask % 4) == 0)),
+                "pgf_linear_bwd_dx: K, ldx, strides must be multiples of 4 and W, dX, mask 16-byte aligned");
+  return linear_bwd_dx(dY, ldy, sdY, W, sW, mask_src, mask_mode, ld_mask, s_mask, dX, ldx, sdX, B, N, K, n_models, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX, float* dW,
+                      long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate, int n_models,
+                      void* stream) {
+  if (n_models == 0) return PGF_OK;
+  PGF_CHECK_ARG(dW && N > 0 && K > 0 && B >= 0, "pgf_linear_bwd_dw: NULL or non-positive argument");
+  if (B == 0) {
+    if (!accumulate) {
+      for (int m = 0; m < n_models; ++m) {
+        cudaMemsetAsync(dW + m * sdW, 0, sizeof(float) * N * K, static_cast<cudaStream_t>(stream));
+        if (db) cudaMemsetAsync(db + m * sdb, 0, sizeof(float) * N, static_cast<cudaStream_t>(stream));
+      }
+    }
+    return PGF_OK;
+  }
+  PGF_CHECK_ARG(dY && X, "pgf_linear_bwd_dw: NULL argument");
+  PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(X) && aligned16(dW) && (sX % 4) == 0 && (sdW % 4) == 0,
+                "pgf_linear_bwd_dw: K, ldx, strides must be multiples of 4 and X, dW 16-byte aligned");
+  LinDwArgs a;
+  a.dY = dY; a.ldy = ldy; a.sdY = sdY; a.X = X; a.ldx = ldx; a.sX = sX; a.dW = dW; a.sdW = sdW; a.db = db; a.sdb = sdb;
+  a.B = B; a.N = N; a.K = K; a.rows_per_cta = 0; a.accumulate = accumulate;
+  return linear_bwd_dw(a, n_models, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
+                  int M, int N, int K, int epi, const float* bias, const void* aux, long long ld_aux, int stream_k,
+                  void* stream) {
+  PGF_CHECK_ARG(A && B && C, "pgf_gemm_bf16: NULL operand");
+  PGF_CHECK_ARG(epi >= 0 && epi <= 6, "pgf_gemm_bf16: bad epilogue %d", epi);
+  if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32)
+    PGF_CHECK_ARG(bias && aligned16(bias), "pgf_gemm_bf16: epilogue needs a 16-byte aligned bias");
+  if (epi == PGF_EPI_RELUMASK_BF16) PGF_CHECK_ARG(aux && aligned16(aux) && (ld_aux % 8) == 0, "pgf_gemm_bf16: epilogue needs aux");
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.aux = aux; g.ld_aux = ld_aux; g.epi = epi;
+  g.stream_k = stream_k;
+  return gemm_bf16(A, lda, a_mn, B, ldb, b_mn, g, static_cast<cudaStream_t>(stream));
+}
+
+size_t pgf_cls_ce_workspace(int B, int H, int n_models) {
+  if (B <= 0 || n_models <= 0) return 0;
+  return cls_ce_workspace(B, H, n_models);
+}
+
+int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const float* Wc, long long sWc, const float* bc,
+               long long sbc, const long long* labels, long long slabels, int B, int H, int n_models, float loss_scale,
+               float grad_scale, int backward, int through_tanh, float* logits, long long slogits, long long* pred,
+               long long spred, float* stats, void* dz, int dz_dtype, long long lddz, long long sdz, float* dWc,
+               long long sdWc, float* dbc, long long sdbc, float* workspace, size_t workspace_bytes, void* stream) {
+  if (n_models == 0) return PGF_OK;
+  PGF_CHECK_ARG(B > 0, "pgf_cls_ce: empty batch (the reference divides by B: cross_entropy mean over 0 rows is NaN)");
+  PGF_CHECK_ARG(h && Wc && bc && workspace, "pgf_cls_ce: NULL argument");
+  PGF_CHECK_ARG(labels || !backward, "pgf_cls_ce: backward needs labels");
+  PGF_CHECK_ARG(aligned16(h) && aligned16(Wc) && (ldh % 4) == 0 && (sWc % 4) == 0 && (sh % 4) == 0,
+                "pgf_cls_ce: h, Wc must be 16-byte aligned");
+  if (backward && dz) PGF_CHECK_ARG(aligned16(dz) && (lddz % 4) == 0 && (sdz % 4) == 0, "pgf_cls_ce: dz must be 16-byte aligned");
+  CeArgs a;
+  a.h = h; a.ldh = ldh; a.sh = sh; a.Wc = Wc; a.sWc = sWc; a.bc = bc; a.sbc = sbc; a.labels = labels; a.slab = slabels;
+  a.logits = logits; a.slogits = slogits; a.pred = pred; a.spred = spred; a.dz = dz; a.lddz = lddz; a.sdz = sdz;
+  a.partial = workspace; a.B = B; a.H = H; a.grad_scale = grad_scale; a.through_tanh = through_tanh;
+  return cls_ce(a, h_dtype, dz_dtype, backward, n_models, loss_scale, stats, dWc, sdWc, dbc, sdbc, workspace, workspace_bytes,
+                static_cast<cudaStream_t>(stream));
+}
+
+int pgf_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  PGF_CHECK_ARG(n >= 0 && step >= 1, "pgf_adam_step: n < 0 or step < 1");
+  if (n == 0) return PGF_OK;
+  PGF_CHECK_ARG(p && g && m && v, "pgf_adam_step: NULL argument");
+  return adam_step(p, g, m, v, bf16_shadow, n, step, lr, beta1, beta2, eps, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n == 0) return PGF_OK;
+  PGF_CHECK_ARG(src && dst && n > 0 && aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "pgf_cast_f32_to_bf16: bad argument");
+  return cast_f32_to_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+size_t pgf_colsum_workspace(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return static_cast<size_t>(colsum_slabs(B, N)) * N * sizeof(float);
+}
+
+int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out, float* workspace, size_t workspace_bytes,
+               void* stream) {
+  PGF_CHECK_ARG(x && out && workspace && B > 0 && N > 0 && (N % 4) == 0, "pgf_colsum: bad argument");
+  return colsum(x, dtype, ld, B, N, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// Kernel (b), large-batch regime: bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA into 128B-swizzled shared memory),
+// with the fusion-MLP epilogues fused in.  Hand-written PTX, no CUTLASS.
+//
+// Reference ops replaced: the cuBLAS SGEMMs behind nn.Linear of `fc_layers` and their autograd
+// (models.py:46-51,80; past_acc.py:87-92,137) when the batch is large enough to be a real dense
+// contraction (SURVEY.md section 8d "Roofline for (b) - tensor pipe").
+//
+//   C[M,N] = A[M,K] . B[N,K]^T        A, B bf16; fp32 accumulate
+// Either operand may be "MN-major" (stored [K,M] / [K,N], i.e. the transposed matrix row-major),
+// which is what the weight-gradient GEMMs need (dW = dZ^T . X contracts over the batch) -- the
+// UMMA descriptors read those layouts directly, no transposed copies are ever materialised.
+//
+// Structure (one CTA per SM, persistent, 192 threads):
+//   warp 0     TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB / stage)
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (128x256x16 per instruction)
+//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time -> bias/activation/mask -> global
+// TMEM holds two 128x256 fp32 accumulators (all 512 columns) so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Work is either whole tiles round-robin, or -- for the K=batch
+// weight-gradient GEMMs whose tile count does not fill 148 SMs -- a stream-K split: the flattened
+// (tile, k-block) space is cut into equal contiguous ranges and partial tiles are combined
+// with fp32 vector reductions into a zero-initialised C.
+#include <cuda.h>
+
+#include "pgf_kernels.cuh"
+
+namespace pgf {
+
+#define PGF_EPI_STORE_BF16 0        // C = acc
+#define PGF_EPI_BIAS_RELU_BF16 1    // C = relu(acc + bias[n])
+#define PGF_EPI_BIAS_TANH_BF16 2    // C = tanh(acc + bias[n])
+#define PGF_EPI_RELUMASK_BF16 3     // C = acc * (aux[m,n] > 0)          (aux bf16 [M,N])
+#define PGF_EPI_ATOMIC_F32 4        // C(fp32) += acc                    (stream-K partials)
+#define PGF_EPI_STORE_F32 5         // C(fp32) = acc
+#define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  Field layout as in the PTX ISA
+// "tcgen05 shared memory descriptor": start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version [46,48), layout_type [61,64) (2 = 128B swizzle).
+//   K-major tile  [rows][64 bf16 = 128 B]: 8-row groups 1024 B apart (SBO); LBO unused (1).
+//   MN-major tile [64 k][64 mn = 128 B] boxes: 8-k groups 1024 B apart (SBO), next 64-wide
+//   MN box 8192 B further (LBO).
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  const uint64_t lbo = MN_MAJOR ? (8192u >> 4) : 1u;
+  const uint64_t sbo = 1024u >> 4;
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct WorkUnit {
+  int tile, kb0, kb1;
+};
+
+struct Scheduler {
+  int num_tiles, kb_total, stream_k;
+  long long cur, end;
+  int it;
+  __device__ Scheduler(const GemmArgs& g) {
+    const int mb = (g.M + BM - 1) / BM, nb = (g.N + BN - 1) / BN;
+    num_tiles = mb * nb;
+    kb_total = (g.K + BK - 1) / BK;
+    stream_k = g.stream_k;
+    it = 0;
+    if (stream_k) {
+      const long long total = static_cast<long long>(num_tiles) * kb_total;
+      const long long per = (total + gridDim.x - 1) / gridDim.x;
+      cur = min(total, per * blockIdx.x);
+      end = min(total, cur + per);
+    } else {
+      cur = end = 0;
+    }
+  }
+  __device__ bool next(WorkUnit& u) {
+    if (stream_k) {
+      if (cur >= end) return false;
+      u.tile = static_cast<int>(cur / kb_total);
+      u.kb0 = static_cast<int>(cur - static_cast<long long>(u.tile) * kb_total);
+      const long long left = end - cur;
+      u.kb1 = static_cast<int>(min(static_cast<long long>(kb_total), u.kb0 + left));
+      cur += u.kb1 - u.kb0;
+      return true;
+    }
+    u.tile = blockIdx.x + it * gridDim.x;
+    ++it;
+    u.kb0 = 0;
+    u.kb1 = kb_total;
+    return u.tile < num_tiles;
+  }
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzle atoms must be 1024-byte aligned
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem slot
+  const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
+  const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES), tempty_bar = smem_u32(bars + 2 * STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb_n = (g.N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      Scheduler sched(g);
+      WorkUnit u;
+      uint32_t stage = 0, phase = 0;
+      while (sched.next(u)) {
+        const int m0 = (u.tile / nb_n) * BM, n0 = (u.tile % nb_n) * BN;
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, fb, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sa, &tmA, fb, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, fb, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(sb, &tmB, fb, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor: fp32 accum, bf16 x bf16, majors, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A_MN) << 15) |
+                             (static_cast<uint32_t>(B_MN) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                             (static_cast<uint32_t>(BM >> 4) << 24);
+      Scheduler sched(g);
+      WorkUnit u;
+      uint32_t stage = 0, phase = 0, unit = 0;
+      while (sched.next(u)) {
+        const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc<A_MN>(sa), bdesc = make_smem_desc<B_MN>(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance along K: K-major +32 B inside the swizzle atom; MN-major +2 k-groups (2 KB)
+            const uint64_t ao = static_cast<uint64_t>((A_MN ? 2048 * k : 32 * k) >> 4);
+            const uint64_t bo = static_cast<uint64_t>((B_MN ? 2048 * k : 32 * k) >> 4);
+            umma_bf16(tmem_d, adesc + ao, bdesc + bo, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);  // accumulator ready for the epilogue
+        ++unit;
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    Scheduler sched(g);
+    WorkUnit u;
+    uint32_t unit = 0;
+    while (sched.next(u)) {
+      const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
+      const int m0 = (u.tile / nb_n) * BM, n0 = (u.tile % nb_n) * BN;
+      const int m = m0 + row_in_tile;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= g.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (m < g.M) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (n + i < g.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n + i));
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+              }
+            }
+            if (g.epi == PGF_EPI_BIAS_RELU_BF16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (g.epi == PGF_EPI_BIAS_TANH_BF16) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+            }
+          } else if (g.epi == PGF_EPI_RELUMASK_BF16) {
+            const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(m) * g.ld_aux + n;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (n + i < g.N) {
+                const uint4 q = *reinterpret_cast<const uint4*>(ax + i);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 h = unpack_bf16x2(w[j]);
+                  f[i + 2 * j] = h.x > 0.f ? f[i + 2 * j] : 0.f;
+                  f[i + 2 * j + 1] = h.y > 0.f ? f[i + 2 * j + 1] : 0.f;
+                }
+              }
+            }
+          }
+          if (g.epi == PGF_EPI_ATOMIC_F32) {
+            float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (n + i < g.N) red_add_v4(cp + i, f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else if (g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32) {
+            float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (n + i < g.N) *reinterpret_cast<float4*>(cp + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+            __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(g.C) + static_cast<long long>(m) * g.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (n + i < g.N) {
+                uint4 q;
+                q.x = pack_bf16x2(f[i], f[i + 1]);
+                q.y = pack_bf16x2(f[i + 2], f[i + 3]);
+                q.z = pack_bf16x2(f[i + 4], f[i + 5]);
+                q.w = pack_bf16x2(f[i + 6], f[i + 7]);
+                *reinterpret_cast<uint4*>(cp + i) = q;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      ++unit;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                     int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
+    return PGF_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", static_cast<int>(r), rows, cols, ld);
+    return PGF_ERR_CUDA;
+  }
+  return PGF_OK;
+}
+
+int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, const GemmArgs& g_in,
+              cudaStream_t s) {
+  GemmArgs g = g_in;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PGF_OK;
+  if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.ldc % 4) ||
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(g.C)) & 15)) {
+    set_error("pgf_gemm_bf16: N, lda, ldb must be multiples of 8, ldc of 4, pointers 16-byte aligned");
+    return PGF_ERR_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
+  rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
+  if (rc != PGF_OK) return rc;
+  rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64) : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN);
+  if (rc != PGF_OK) return rc;
+
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int kb_total = (g.K + BK - 1) / BK;
+  const int sms = num_sms();
+  int grid;
+  if (g.stream_k) {
+    if (g.epi != PGF_EPI_ATOMIC_F32) {
+      set_error("pgf_gemm_bf16: stream-K needs the fp32 reduction epilogue");
+      return PGF_ERR_ARG;
+    }
+    const long long total = static_cast<long long>(tiles) * kb_total;
+    grid = static_cast<int>(total < sms ? total : sms);
+  } else {
+    grid = tiles < sms ? tiles : sms;
+  }
+#define PGF_GEMM_LAUNCH(AM, BMN)                                                                                       \
+  do {                                                                                                                 \
+    cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);  \
+    gemm_bf16_tc_kernel<AM, BMN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(tmA, tmB, g);                             \
+  } while (0)
+  if (a_mn && b_mn) PGF_GEMM_LAUNCH(true, true);
+  else if (a_mn) PGF_GEMM_LAUNCH(true, false);
+  else if (b_mn) PGF_GEMM_LAUNCH(false, true);
+  else PGF_GEMM_LAUNCH(false, false);
+#undef PGF_GEMM_LAUNCH
+  PGF_CUDA_LAUNCH_CHECK("pgf_gemm_bf16");
+  return PGF_OK;
+}
+
+}  // namespace pgf

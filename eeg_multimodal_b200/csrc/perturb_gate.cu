@@ -1,0 +1,493 @@
+// Kernel (a): fused concat -> row min-max normalise -> Laplace perturbation -> Gumbel gate.
+//
+// Reference ops replaced (python/src/custom_models/models.py, == past_acc.py:120-136):
+//   :69  torch.cat of the feature blocks
+//   :70-72 row min / row max / (x-min)/(max-min)          (no epsilon guard, NaN on constant row)
+//   :74  Laplace(0,1).sample on the HOST + .to(device)    -> Philox in-kernel, or injected tensor
+//   :76  feature + noise * eps_hat
+//   :77-79 gumbel_softmax over the stacked (w, 1-w) planes and (feature*mask).sum(0)
+// One warp owns one row: the whole row (<= 4096 floats) lives in registers, min/max are
+// warp-shuffle reductions, every global access is a coalesced 128-bit load/store, and the
+// per-column coefficients (eps_hat, w) are staged once per CTA in shared memory.
+//
+// HBM traffic per row (Philox mode): read 4*D, write 4*D (fp32 out) or 2*D (bf16 out).
+#include "pgf_kernels.cuh"
+#include "philox.cuh"
+
+namespace pgf {
+
+
+template <typename OutT>
+__device__ __forceinline__ void store_out4(void* out, long long off, const float4& v);
+template <>
+__device__ __forceinline__ void store_out4<float>(void* out, long long off, const float4& v) {
+  stg_stream(reinterpret_cast<float4*>(static_cast<float*>(out) + off), v);
+}
+template <>
+__device__ __forceinline__ void store_out4<__nv_bfloat16>(void* out, long long off, const float4& v) {
+  uint2 p;
+  p.x = pack_bf16x2(v.x, v.y);
+  p.y = pack_bf16x2(v.z, v.w);
+  stg_stream_u2(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + off), p);
+}
+
+// faithful two-plane softmax gate on one element (injected mode): returns gated value and index
+__device__ __forceinline__ float gate_faithful(float f, float w, float g0, float g1, float tau, int hard, int& idx) {
+  const float z0 = __fdiv_rn(__fadd_rn(w, g0), tau);
+  const float z1 = __fdiv_rn(__fadd_rn(__fsub_rn(1.0f, w), g1), tau);
+  const float m = fmaxf(z0, z1);
+  const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+  const float s = __fadd_rn(e0, e1);
+  const float y0 = __fdiv_rn(e0, s), y1 = __fdiv_rn(e1, s);
+  idx = (y1 > y0) ? 1 : 0;  // argmax over dim 0, first index on ties
+  float m0 = y0, m1 = y1;
+  if (hard) {  // y_hard - y_soft.detach() + y_soft
+    m0 = __fadd_rn(__fsub_rn(idx == 0 ? 1.0f : 0.0f, y0), y0);
+    m1 = __fadd_rn(__fsub_rn(idx == 1 ? 1.0f : 0.0f, y1), y1);
+  }
+  return __fadd_rn(__fmul_rn(f, m0), __fmul_rn(f, m1));
+}
+
+template <int NV, int NOISE, typename OutT, bool WANT_GATE>
+__global__ void __launch_bounds__(256) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
+  extern __shared__ float4 smem4[];
+  float4* s_eps = smem4;                 // [D/4]
+  float4* s_w = smem4 + (a.D >> 2);      // [D/4] (only when the gate is evaluated)
+  const int nvec = a.D >> 2;
+  if (NOISE != PGF_NOISE_NONE) {
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+      s_eps[i] = reinterpret_cast<const float4*>(a.eps_hat)[i];
+      if (WANT_GATE) s_w[i] = reinterpret_cast<const float4*>(a.w)[i];
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int d01 = a.d[0] + a.d[1];
+  const unsigned int k0 = static_cast<unsigned int>(a.seed), k1 = static_cast<unsigned int>(a.seed >> 32);
+
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); row < a.B;
+       row += static_cast<long long>(gridDim.x) * warps_per_cta) {
+    float4 v[NV];
+    float mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;
+    // ---- fused concat load (models.py:69): all loads issued before first use
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.D) {
+        const float* p;
+        if (col < a.d[0])
+          p = a.x[0] + row * a.ld[0] + col;
+        else if (col < d01)
+          p = a.x[1] + row * a.ld[1] + (col - a.d[0]);
+        else
+          p = a.x[2] + row * a.ld[2] + (col - d01);
+        v[k] = ldg_stream(reinterpret_cast<const float4*>(p));
+      }
+    }
+    // ---- row min / max (models.py:70-71); torch.min/max propagate NaN
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.D) {
+        mn = fminf(fminf(mn, v[k].x), fminf(v[k].y, fminf(v[k].z, v[k].w)));
+        mx = fmaxf(fmaxf(mx, v[k].x), fmaxf(v[k].y, fmaxf(v[k].z, v[k].w)));
+        has_nan |= (v[k].x != v[k].x) | (v[k].y != v[k].y) | (v[k].z != v[k].z) | (v[k].w != v[k].w);
+      }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (__any_sync(0xffffffffu, has_nan)) mn = mx = __int_as_float(0x7fc00000);
+    const float range = __fsub_rn(mx, mn);
+    const float inv_range = __frcp_rn(range);
+    if (lane == 0) {
+      if (a.row_min) a.row_min[row] = mn;
+      if (a.row_max) a.row_max[row] = mx;
+    }
+    const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      const int col = j << 2;
+      if (col < a.D) {
+        float f[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        // ---- normalise (models.py:72).  Parity modes use the exact IEEE division the
+        // reference does; Philox mode multiplies by the reciprocal (<= 1 ulp apart).
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (NOISE == PGF_NOISE_PHILOX)
+            f[e] = __fmul_rn(__fsub_rn(f[e], mn), inv_range);
+          else
+            f[e] = __fdiv_rn(__fsub_rn(f[e], mn), range);
+        }
+        int idx[4] = {0, 0, 0, 0};
+        if (NOISE == PGF_NOISE_INJECTED) {
+          const float4 e4 = s_eps[j];
+          const float eh[4] = {e4.x, e4.y, e4.z, e4.w};
+          const float4 l4 = ldg_stream(reinterpret_cast<const float4*>(a.lap + row * a.D + col));
+          const float lp[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[e] = __fadd_rn(f[e], __fmul_rn(lp[e], eh[e]));  // :76
+          if (WANT_GATE) {                                                               // :77-79
+            const float4 w4 = s_w[j];
+            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float4 g0 = ldg_stream(reinterpret_cast<const float4*>(a.gum + row * a.D + col));
+            const float4 g1 =
+                ldg_stream(reinterpret_cast<const float4*>(a.gum + (static_cast<long long>(a.B) + row) * a.D + col));
+            const float ga[4] = {g0.x, g0.y, g0.z, g0.w}, gb[4] = {g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[e] = gate_faithful(f[e], ww[e], ga[e], gb[e], a.tau, a.hard, idx[e]);
+          }
+        } else if (NOISE == PGF_NOISE_PHILOX) {
+          const float4 e4 = s_eps[j];
+          const float eh[4] = {e4.x, e4.y, e4.z, e4.w};
+          const uint4 r = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
+          const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[e] = fmaf(laplace_from_bits(rb[e]), eh[e], f[e]);
+          if (WANT_GATE) {
+            // The two mask planes sum to one (hard: exactly, soft: within 1 ulp), so the gated
+            // value IS the perturbed value; only the gate index is a real output.
+            const float4 w4 = s_w[j];
+            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+            const uint4 q0 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL0, a.offset, k0, k1);
+            const uint4 q1 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL1, a.offset, k0, k1);
+            const unsigned int qa[4] = {q0.x, q0.y, q0.z, q0.w}, qb[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float z0 = (ww[e] + gumbel_from_bits(qa[e])) * a.inv_tau;
+              const float z1 = ((1.0f - ww[e]) + gumbel_from_bits(qb[e])) * a.inv_tau;
+              idx[e] = z1 > z0 ? 1 : 0;
+            }
+          }
+        }
+        store_out4<OutT>(a.out, row * a.ld_out + col, make_float4(f[0], f[1], f[2], f[3]));
+        if (WANT_GATE && a.gate_idx) {
+          const unsigned int packed = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+          *reinterpret_cast<unsigned int*>(a.gate_idx + row * a.D + col) = packed;
+        }
+      }
+    }
+  }
+}
+
+template <int NV, int NOISE, typename OutT>
+static int launch_fwd_gate(const PerturbFwdArgs& a, bool want_gate, cudaStream_t stream) {
+  const int threads = 256;
+  int grid = num_sms() * 2;
+  const int max_grid = (a.B + 7) / 8;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  const size_t smem = (NOISE == PGF_NOISE_NONE) ? 0 : static_cast<size_t>(a.D) * sizeof(float) * (want_gate ? 2 : 1);
+  if (want_gate)
+    perturb_gate_fwd_kernel<NV, NOISE, OutT, true><<<grid, threads, smem, stream>>>(a);
+  else
+    perturb_gate_fwd_kernel<NV, NOISE, OutT, false><<<grid, threads, smem, stream>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_fwd");
+  return PGF_OK;
+}
+
+template <int NV>
+static int launch_fwd_nv(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
+#define PGF_DISPATCH_OUT(NOISE)                                                              \
+  return out_dtype == PGF_DT_F32 ? launch_fwd_gate<NV, NOISE, float>(a, want_gate, s)         \
+                                 : launch_fwd_gate<NV, NOISE, __nv_bfloat16>(a, want_gate, s)
+  switch (noise) {
+    case PGF_NOISE_INJECTED: PGF_DISPATCH_OUT(PGF_NOISE_INJECTED);
+    case PGF_NOISE_PHILOX: PGF_DISPATCH_OUT(PGF_NOISE_PHILOX);
+    default: PGF_DISPATCH_OUT(PGF_NOISE_NONE);
+  }
+#undef PGF_DISPATCH_OUT
+}
+
+int perturb_gate_fwd(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
+  const int nv = (a.D / 4 + 31) / 32;
+  if (nv <= 8) return launch_fwd_nv<8>(a, noise, out_dtype, want_gate, s);
+  if (nv <= 20) return launch_fwd_nv<20>(a, noise, out_dtype, want_gate, s);
+  if (nv <= 32) return launch_fwd_nv<32>(a, noise, out_dtype, want_gate, s);
+  set_error("pgf_perturb_gate_fwd: fused width D=%d exceeds the register-resident limit 4096", a.D);
+  return PGF_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward wrt DP:  dDP[d] = deps_dDP[d] * sum_b dF[b,d] * lap[b,d]
+// (reference: autograd through models.py:75-76; the gate's own contribution is zero in exact
+//  arithmetic because both mask planes multiply the same feature -- SURVEY.md section 0 item 4)
+// Stage 1: each CTA column-reduces a slab of rows for 512 columns into partial[slab][D].
+// Stage 2: deterministic sum over slabs, times the per-column coefficient.
+// ------------------------------------------------------------------------------------------
+struct PerturbBwdArgs {
+  const void* dF;
+  long long ld;
+  int B, D;
+  const float* lap;
+  unsigned long long seed;
+  unsigned int offset;
+  unsigned long long row0;
+  int rows_per_slab;
+  float* partial;  // [nslab, D]
+};
+
+template <typename InT>
+__device__ __forceinline__ float4 load_in4(const void* p, long long off);
+template <>
+__device__ __forceinline__ float4 load_in4<float>(const void* p, long long off) {
+  return ldg_stream(reinterpret_cast<const float4*>(static_cast<const float*>(p) + off));
+}
+template <>
+__device__ __forceinline__ float4 load_in4<__nv_bfloat16>(const void* p, long long off) {
+  const uint2 u = ldg_stream_u2(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p) + off));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <int NOISE, typename InT>
+__global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column index
+  const int col = j << 2;
+  if (col >= a.D) return;
+  const int slab = blockIdx.y;
+  const int r0 = slab * a.rows_per_slab;
+  const int r1 = min(a.B, r0 + a.rows_per_slab);
+  const unsigned int k0 = static_cast<unsigned int>(a.seed), k1 = static_cast<unsigned int>(a.seed >> 32);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 4;
+  int r = r0;
+  for (; r + U <= r1; r += U) {
+    float4 g[U], l[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = load_in4<InT>(a.dF, static_cast<long long>(r + u) * a.ld + col);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (NOISE == PGF_NOISE_INJECTED) {
+        l[u] = ldg_stream(reinterpret_cast<const float4*>(a.lap + static_cast<long long>(r + u) * a.D + col));
+      } else {
+        const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
+                                      PGF_STREAM_LAPLACE, a.offset, k0, k1);
+        l[u] = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z),
+                           laplace_from_bits(q.w));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc.x = fmaf(g[u].x, l[u].x, acc.x);
+      acc.y = fmaf(g[u].y, l[u].y, acc.y);
+      acc.z = fmaf(g[u].z, l[u].z, acc.z);
+      acc.w = fmaf(g[u].w, l[u].w, acc.w);
+    }
+  }
+  for (; r < r1; ++r) {
+    const float4 g = load_in4<InT>(a.dF, static_cast<long long>(r) * a.ld + col);
+    float4 l;
+    if (NOISE == PGF_NOISE_INJECTED) {
+      l = ldg_stream(reinterpret_cast<const float4*>(a.lap + static_cast<long long>(r) * a.D + col));
+    } else {
+      const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
+                                    PGF_STREAM_LAPLACE, a.offset, k0, k1);
+      l = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z), laplace_from_bits(q.w));
+    }
+    acc.x = fmaf(g.x, l.x, acc.x);
+    acc.y = fmaf(g.y, l.y, acc.y);
+    acc.z = fmaf(g.z, l.z, acc.z);
+    acc.w = fmaf(g.w, l.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(a.partial + static_cast<long long>(slab) * a.D + col) = acc;
+}
+
+__global__ void perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
+                                               const float* __restrict__ coef, float* __restrict__ dDP,
+                                               float accumulate) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int i = 0; i < nslab; ++i) s += partial[static_cast<long long>(i) * D + d];
+  const float v = s * coef[d];
+  dDP[d] = accumulate != 0.f ? dDP[d] + v : v;
+}
+
+int perturb_bwd_slabs(int B, int D) {
+  const int col_ctas = (D / 4 + 127) / 128;
+  int slabs = (num_sms() * 4 + col_ctas - 1) / col_ctas;
+  const int max_slabs = (B + 31) / 32;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  return slabs;
+}
+
+int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, int B, int D, int noise, const float* lap,
+                        unsigned long long seed, unsigned int offset, unsigned long long row0, const float* coef,
+                        float* workspace, size_t workspace_bytes, float* dDP, int accumulate, cudaStream_t s) {
+  const int slabs = perturb_bwd_slabs(B, D);
+  if (workspace_bytes < static_cast<size_t>(slabs) * D * sizeof(float)) {
+    set_error("pgf_perturb_gate_bwd_dp: workspace too small (%zu < %zu bytes)", workspace_bytes,
+              static_cast<size_t>(slabs) * D * sizeof(float));
+    return PGF_ERR_WORKSPACE;
+  }
+  PerturbBwdArgs a;
+  a.dF = dF;
+  a.ld = ld;
+  a.B = B;
+  a.D = D;
+  a.lap = lap;
+  a.seed = seed;
+  a.offset = offset;
+  a.row0 = row0;
+  a.rows_per_slab = (B + slabs - 1) / slabs;
+  a.partial = workspace;
+  const dim3 grid((D / 4 + 127) / 128, slabs);
+  if (noise == PGF_NOISE_INJECTED) {
+    if (dtype == PGF_DT_F32)
+      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float><<<grid, 128, 0, s>>>(a);
+    else
+      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16><<<grid, 128, 0, s>>>(a);
+  } else {
+    if (dtype == PGF_DT_F32)
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float><<<grid, 128, 0, s>>>(a);
+    else
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16><<<grid, 128, 0, s>>>(a);
+  }
+  PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
+  perturb_bwd_dp_finalize_kernel<<<(D + 255) / 256, 256, 0, s>>>(workspace, slabs, D, coef, dDP,
+                                                                accumulate ? 1.f : 0.f);
+  PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp(finalize)");
+  return PGF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-column coefficients from DP (models.py:73,75): w = sigmoid(DP),
+//   eps_hat = 1/log((e^eps - w)/(1 - w))    [fixed]      or   log(...)   [unfixed, model.py:57]
+//   deps_dDP = d eps_hat / d DP = d eps_hat/dw * w(1-w)
+//     fixed:   -(E-1) w / (L^2 (E-w)),    unfixed:  (E-1) w / (E-w),   L = log((E-w)/(1-w))
+// ------------------------------------------------------------------------------------------
+__global__ void dp_coeffs_kernel(const float* __restrict__ DP, float exp_eps, int fixed, int D, float* __restrict__ w_out,
+                                 float* __restrict__ eps_hat, float* __restrict__ deps) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float x = DP[d];
+  const float w = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  const float num = __fsub_rn(exp_eps, w);
+  const float ratio = __fdiv_rn(num, __fsub_rn(1.0f, w));
+  const float L = logf(ratio);
+  if (w_out) w_out[d] = w;
+  if (eps_hat) eps_hat[d] = fixed ? __fdiv_rn(1.0f, L) : L;
+  if (deps) {
+    const float t = (exp_eps - 1.0f) * w / num;
+    deps[d] = fixed ? -t / (L * L) : t;
+  }
+}
+
+int dp_coeffs(const float* DP, float exp_eps, int fixed, int D, float* w, float* eps_hat, float* deps, cudaStream_t s) {
+  dp_coeffs_kernel<<<(D + 255) / 256, 256, 0, s>>>(DP, exp_eps, fixed, D, w, eps_hat, deps);
+  PGF_CUDA_LAUNCH_CHECK("pgf_dp_coeffs");
+  return PGF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward of the min-max normalisation wrt the raw feature blocks (only needed when the
+// encoders above the head are trained, reference: autograd through models.py:70-72):
+//   n = (x-mn)/r, r = mx-mn;  dx_j = dn_j/r - [j==argmin] sum_k dn_k (1-n_k)/r - [j==argmax] sum_k dn_k n_k / r
+// torch.min/max(dim) route the gradient to the single index they return (first occurrence).
+// ------------------------------------------------------------------------------------------
+
+template <int NV, typename InT>
+__global__ void __launch_bounds__(256) minmax_norm_bwd_kernel(const NormBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int d01 = a.d[0] + a.d[1];
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); row < a.B;
+       row += static_cast<long long>(gridDim.x) * warps_per_cta) {
+    float4 v[NV];
+    float mn = INFINITY, mx = -INFINITY;
+    int imn = 0x7fffffff, imx = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.D) {
+        const float* p = col < a.d[0] ? a.x[0] + row * a.ld[0] + col
+                                      : (col < d01 ? a.x[1] + row * a.ld[1] + (col - a.d[0])
+                                                   : a.x[2] + row * a.ld[2] + (col - d01));
+        v[k] = *reinterpret_cast<const float4*>(p);
+        const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e[q] < mn) { mn = e[q]; imn = col + q; }
+          if (e[q] > mx) { mx = e[q]; imx = col + q; }
+        }
+      }
+    }
+    // warp arg-min / arg-max, first occurrence on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float omn = __shfl_xor_sync(0xffffffffu, mn, o);
+      const int oimn = __shfl_xor_sync(0xffffffffu, imn, o);
+      if (omn < mn || (omn == mn && oimn < imn)) { mn = omn; imn = oimn; }
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oimx = __shfl_xor_sync(0xffffffffu, imx, o);
+      if (omx > mx || (omx == mx && oimx < imx)) { mx = omx; imx = oimx; }
+    }
+    const float r = mx - mn;
+    const float inv_r = 1.0f / r;
+    float4 g[NV];
+    float s_min = 0.f, s_max = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.D) {
+        g[k] = load_in4<InT>(a.dn, row * a.ld_dn + col);
+        const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        const float ge[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float n = (e[q] - mn) * inv_r;
+          s_max += ge[q] * n;
+          s_min += ge[q] * (1.0f - n);
+        }
+      }
+    }
+    s_min = warp_sum(s_min) * inv_r;
+    s_max = warp_sum(s_max) * inv_r;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.D) {
+        float o[4] = {g[k].x * inv_r, g[k].y * inv_r, g[k].z * inv_r, g[k].w * inv_r};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (col + q == imn) o[q] -= s_min;
+          if (col + q == imx) o[q] -= s_max;
+        }
+        float* p = col < a.d[0] ? a.dx[0] + row * a.ld_dx[0] + col
+                                : (col < d01 ? a.dx[1] + row * a.ld_dx[1] + (col - a.d[0])
+                                             : a.dx[2] + row * a.ld_dx[2] + (col - d01));
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+template <int NV>
+static int launch_norm_bwd(const NormBwdArgs& a, int dtype, cudaStream_t s) {
+  int grid = num_sms() * 2;
+  const int max_grid = (a.B + 7) / 8;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  if (dtype == PGF_DT_F32)
+    minmax_norm_bwd_kernel<NV, float><<<grid, 256, 0, s>>>(a);
+  else
+    minmax_norm_bwd_kernel<NV, __nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_minmax_norm_bwd");
+  return PGF_OK;
+}
+
+int minmax_norm_bwd(const NormBwdArgs& a, int dtype, cudaStream_t s) {
+  const int nv = (a.D / 4 + 31) / 32;
+  if (nv <= 8) return launch_norm_bwd<8>(a, dtype, s);
+  if (nv <= 20) return launch_norm_bwd<20>(a, dtype, s);
+  if (nv <= 32) return launch_norm_bwd<32>(a, dtype, s);
+  set_error("pgf_minmax_norm_bwd: fused width D=%d exceeds the register-resident limit 4096", a.D);
+  return PGF_ERR_UNSUPPORTED;
+}
+
+}  // namespace pgf

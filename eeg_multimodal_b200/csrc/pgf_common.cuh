@@ -1,0 +1,104 @@
+// Shared device/host helpers for the pgfuse kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pgfuse kernels are written for sm_100a (B200) only"
+#endif
+
+#define PGF_OK 0
+#define PGF_ERR_ARG 1
+#define PGF_ERR_CUDA 2
+#define PGF_ERR_UNSUPPORTED 3
+#define PGF_ERR_WORKSPACE 4
+
+#define PGF_DT_F32 0
+#define PGF_DT_BF16 1
+
+// noise modes of the perturb/gate kernel
+#define PGF_NOISE_INJECTED 0  // Laplace / Gumbel tensors supplied by the caller (parity tests)
+#define PGF_NOISE_PHILOX 1    // counter-based Philox4x32-10 (production)
+#define PGF_NOISE_NONE 2      // non-private ConcatModel path (reference model.py:53-64)
+
+namespace pgf {
+
+void set_error(const char* fmt, ...);
+
+#define PGF_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      pgf::set_error(__VA_ARGS__);        \
+      return PGF_ERR_ARG;                 \
+    }                                     \
+  } while (0)
+
+#define PGF_CUDA_LAUNCH_CHECK(name)                                              \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      pgf::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__)); \
+      return PGF_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+#define PGF_CUDA_CALL(call)                                                      \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      pgf::set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return PGF_ERR_CUDA;                                                       \
+    }                                                                            \
+  } while (0)
+
+int num_sms();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit global accesses (data touched once: keep it out of L1)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_u2(uint2* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+}  // namespace pgf

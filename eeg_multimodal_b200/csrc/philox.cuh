@@ -1,0 +1,46 @@
+// Counter-based noise for the perturb/gate kernels: Philox4x32-10 keyed per
+// (column group, global row, stream, offset).  Bit-for-bit definition: oracle/philox_ref.py.
+// Replaces the reference's sequential global-RNG draws (models.py:74 Laplace.sample on the
+// host + H2D copy; models.py:77 exponential_() inside F.gumbel_softmax).
+#pragma once
+#include <stdint.h>
+
+namespace pgf {
+
+#define PGF_STREAM_LAPLACE 0u
+#define PGF_STREAM_GUMBEL0 1u
+#define PGF_STREAM_GUMBEL1 2u
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += W0;
+    k1 += W1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Laplace(0,1): sign bit + 23-bit magnitude uniform, v=(m+0.5)*2^-23 exact in fp32.
+__device__ __forceinline__ float laplace_from_bits(uint32_t r) {
+  const float v = (static_cast<float>((r >> 8) & 0x7FFFFFu) + 0.5f) * 1.1920928955078125e-07f;
+  const float mag = -__logf(v);
+  return (r >> 31) ? -mag : mag;
+}
+
+// Gumbel(0,1) = -log(Exp(1)), Exp(1) = -log(v), v=((r>>9)+0.5)*2^-23.
+__device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
+  const float v = (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  return -__logf(-__logf(v));
+}
+
+}  // namespace pgf

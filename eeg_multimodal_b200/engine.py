@@ -1,0 +1,265 @@
+"""Training / evaluation engine for one or many independent heads (the eps x seed sweep).
+
+Implements the reference's step structure without autograd, on preallocated device buffers:
+
+    pass 1  hard=False -> loss -> backward -> Adam(DP)            past_acc.py:198-203
+    pass 2  hard=True  -> loss -> backward -> Adam(everything else) past_acc.py:206-212
+    eval    hard=True, noise still on, no grad                     past_acc.py:218-228
+
+Pass 1 only needs the dX chain and dDP, pass 2 only the weight gradients: the gradients the
+reference computes and then discards (`zero_grad` at past_acc.py:206 / :198) are never formed.
+
+Two arithmetic modes:
+  precision='fp32'  all models advance together through the GROUPED fp32 CUDA-core kernels
+                    (reference batch size, weight-streaming bound; parity mode, 1e-5)
+  precision='bf16'  each model runs the tcgen05 GEMM path (large batch; bf16 operands, fp32
+                    accumulate, fp32 master weights + Adam; 2e-2 bar)
+
+Parameter layout per model: one flat fp32 buffer [W1 | b1 | W2 | b2 | Wc | bc | pad] so the
+optimiser is a single launch; `state_dict(i)` / `load_state_dict(i, sd)` use the reference's
+key names (fc_layers.0.weight ... DP).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .model import REFERENCE_SEED, exp_eps_of
+
+
+class HeadEngine:
+    def __init__(self, n_models=1, feature_dims=(768, 768, 768), hidden=768, eps=1.0, seeds=None, lr=1e-6,
+                 precision="fp32", fixed_formula=True, tau=1.0, device="cuda", init_seed=REFERENCE_SEED,
+                 noise="philox", betas=(0.9, 0.999), adam_eps=1e-8, dp_init=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HeadEngine needs a CUDA device: there is no CPU fallback")
+        assert precision in ("fp32", "bf16")
+        self.M = int(n_models)
+        self.dims = tuple(int(d) for d in feature_dims)
+        self.D, self.H, self.C = sum(self.dims), int(hidden), 2
+        self.device = torch.device(device)
+        self.precision, self.fixed, self.tau, self.lr = precision, bool(fixed_formula), float(tau), float(lr)
+        self.betas, self.adam_eps = betas, adam_eps
+        self.noise = noise
+        eps_list = list(eps) if isinstance(eps, (list, tuple)) else [eps] * self.M
+        assert len(eps_list) == self.M
+        self.eps = eps_list
+        self.exp_eps = [exp_eps_of(e) for e in eps_list]
+        self.seeds = list(seeds) if seeds is not None else [REFERENCE_SEED + i for i in range(self.M)]
+        D, H, C = self.D, self.H, self.C
+        sizes = [("W1", (D, D)), ("b1", (D,)), ("W2", (H, D)), ("b2", (H,)), ("Wc", (C, H)), ("bc", (C,))]
+        self.layout, off = {}, 0
+        for name, shape in sizes:
+            n = math.prod(shape)
+            self.layout[name] = (off, shape)
+            off += (n + 7) // 8 * 8  # 16-byte aligned segments in fp32 AND in the bf16 shadow (TMA)
+        self.P = off
+        dev = self.device
+        self.flat = torch.zeros(self.M, self.P, device=dev)
+        self.grad = torch.zeros(self.M, self.P, device=dev)
+        self.m = torch.zeros(self.M, self.P, device=dev)
+        self.v = torch.zeros(self.M, self.P, device=dev)
+        self.DP = torch.zeros(self.M, D, device=dev)
+        self.dDP = torch.zeros(self.M, D, device=dev)
+        self.DP_m = torch.zeros(self.M, D, device=dev)
+        self.DP_v = torch.zeros(self.M, D, device=dev)
+        self.shadow = torch.zeros(self.M, self.P, device=dev, dtype=torch.bfloat16) if precision == "bf16" else None
+        self.t_model = 0
+        self.t_dp = 0
+        self.noise_offset = 0
+        self._bufs = {}
+        self._injected = None
+        self._init_params(init_seed, dp_init)
+
+    # ---- parameters ----------------------------------------------------------------------------
+    def view(self, name, src=None):
+        off, shape = self.layout[name]
+        src = self.flat if src is None else src
+        return src[:, off:off + math.prod(shape)].view(self.M, *shape)
+
+    def _init_params(self, init_seed, dp_init):
+        """nn.Linear default init (kaiming-uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))),
+        one CPU generator per model so a model's init does not depend on the ensemble size."""
+        for i in range(self.M):
+            g = torch.Generator().manual_seed(int(init_seed) + i)
+            for wn, bn in (("W1", "b1"), ("W2", "b2"), ("Wc", "bc")):
+                _, shape = self.layout[wn]
+                k = 1.0 / math.sqrt(shape[1])
+                self.view(wn)[i].copy_((torch.rand(shape, generator=g) * 2 - 1) * k)
+                self.view(bn)[i].copy_((torch.rand(shape[0], generator=g) * 2 - 1) * k)
+            if dp_init is not None:
+                self.DP[i].copy_(torch.as_tensor(dp_init, dtype=torch.float32).reshape(-1))
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        if self.shadow is not None:
+            ops.cast_bf16(self.flat, self.shadow)
+
+    _KEYS = {"fc_layers.0.weight": "W1", "fc_layers.0.bias": "b1", "fc_layers.2.weight": "W2",
+             "fc_layers.2.bias": "b2", "classifier.weight": "Wc", "classifier.bias": "bc"}
+
+    def state_dict(self, i=0):
+        sd = {k: self.view(n)[i].detach().clone() for k, n in self._KEYS.items()}
+        sd["DP"] = self.DP[i].detach().clone().view(1, self.D)
+        return sd
+
+    def load_state_dict(self, i, sd, strict=False):
+        missing = []
+        for k, n in self._KEYS.items():
+            if k in sd:
+                self.view(n)[i].copy_(sd[k])
+            else:
+                missing.append(k)
+        if "DP" in sd:
+            self.DP[i].copy_(sd["DP"].reshape(-1))
+        else:
+            missing.append("DP")
+        if strict and missing:
+            raise KeyError(f"missing keys {missing}")
+        self.sync_shadow()
+        return missing
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _buf(self, name, shape, dtype):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def inject_noise(self, lap, gum=None):
+        """Per-model injected noise for the NEXT pass: lap [M,B,D], gum [M,2,B,D] (parity tests)."""
+        self._injected = (lap.contiguous(), None if gum is None else gum.contiguous())
+
+    def _perturb(self, blocks, hard, out, row0, want_coeffs=True):
+        """kernel (a) for every model; returns the per-model deps_dDP rows and the noise spec."""
+        M, D = self.M, self.D
+        coef = self._buf("coef", (M, 3, D), torch.float32)
+        inj = self._injected
+        self._injected = None
+        offset = self.noise_offset
+        self.noise_offset += 1
+        for i in range(M):
+            L.call("pgf_dp_coeffs", self.DP[i].data_ptr(), self.exp_eps[i], int(self.fixed), D, coef[i, 0].data_ptr(),
+                   coef[i, 1].data_ptr(), coef[i, 2].data_ptr(), ops._stream())
+            bl = [b[i] if b.dim() == 3 else b for b in blocks]
+            if inj is not None:
+                ops.perturb_gate_fwd(bl, coef[i, 0], coef[i, 1], noise_mode=L.NOISE_INJECTED, lap=inj[0][i],
+                                     gum=None if inj[1] is None else inj[1][i], tau=self.tau, hard=hard,
+                                     want_gate=inj[1] is not None, out=out[i])
+            else:
+                ops.perturb_gate_fwd(bl, coef[i, 0], coef[i, 1], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i],
+                                     offset=offset, row0=row0, tau=self.tau, hard=hard, want_gate=False, out=out[i])
+        return coef, (inj, offset)
+
+    def _dDP(self, dX, coef, noise_spec, row0):
+        inj, offset = noise_spec
+        for i in range(self.M):
+            if inj is not None:
+                ops.perturb_gate_bwd_dp(dX[i], coef[i, 2], noise_mode=L.NOISE_INJECTED, lap=inj[0][i], out=self.dDP[i])
+            else:
+                ops.perturb_gate_bwd_dp(dX[i], coef[i, 2], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
+                                        row0=row0, out=self.dDP[i])
+
+    def _labels(self, labels):
+        labels = labels.reshape(labels.shape[0], -1)[:, 0] if labels.dim() == 2 and labels.shape[-1] == 1 else labels
+        return labels.contiguous()
+
+    # ---- one forward(+backward) pass -----------------------------------------------------------
+    def _pass(self, blocks, labels, hard, mode, row0=0, global_batch=None):
+        """mode: 'dp' (pass 1), 'model' (pass 2) or 'eval'.  Returns the cls_ce result dict."""
+        B = blocks[0].shape[-2]
+        M, D, H = self.M, self.D, self.H
+        gb = float(global_batch or B)
+        W1, b1, W2, b2, Wc, bc = (self.view(n) for n in ("W1", "b1", "W2", "b2", "Wc", "bc"))
+        backward = mode != "eval"
+        if self.precision == "fp32":
+            X = self._buf("X", (M, B, D), torch.float32)
+            coef, nspec = self._perturb(blocks, hard, X, row0)
+            H1 = ops.linear_fwd(X, W1, b1, L.ACT_RELU, out=self._buf("H1", (M, B, D), torch.float32))
+            H2 = ops.linear_fwd(H1, W2, b2, L.ACT_TANH, out=self._buf("H2", (M, B, H), torch.float32))
+            res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
+                             dz=self._buf("dZ2", (M, B, H), torch.float32) if backward else None,
+                             dWc=self.view("Wc", self.grad) if mode == "model" else None,
+                             dbc=self.view("bc", self.grad) if mode == "model" else None)
+            if mode == "eval":
+                return res
+            dZ2 = res["dz"]
+            dZ1 = ops.linear_bwd_dx(dZ2, W2, mask_src=H1, mask_mode=L.ACT_RELU, out=self._buf("dZ1", (M, B, D), torch.float32))
+            if mode == "dp":
+                dX = ops.linear_bwd_dx(dZ1, W1, out=self._buf("dX", (M, B, D), torch.float32))
+                self._dDP(dX, coef, nspec, row0)
+            else:
+                ops.linear_bwd_dw(dZ2, H1, dW=self.view("W2", self.grad), db=self.view("b2", self.grad))
+                ops.linear_bwd_dw(dZ1, X, dW=self.view("W1", self.grad), db=self.view("b1", self.grad))
+            return res
+        # ---- bf16 tensor-core path, one model at a time
+        bf = torch.bfloat16
+        X = self._buf("Xh", (M, B, D), bf)
+        coef, nspec = self._perturb(blocks, hard, X, row0)
+        H1 = self._buf("H1h", (M, B, D), bf)
+        H2 = self._buf("H2h", (M, B, H), bf)
+        W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
+        for i in range(M):
+            ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i])
+            ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_BF16, bias=b2[i])
+        res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
+                         dz=self._buf("dZ2h", (M, B, H), bf) if backward else None,
+                         dWc=self.view("Wc", self.grad) if mode == "model" else None,
+                         dbc=self.view("bc", self.grad) if mode == "model" else None)
+        if mode == "eval":
+            return res
+        dZ2 = res["dz"]
+        dZ1 = self._buf("dZ1h", (M, B, D), bf)
+        for i in range(M):
+            # dZ1 = (dZ2 . W2) * relu'(H1):   B operand = W2 stored [K=H, N=D]  -> MN-major
+            ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1[i])
+        if mode == "dp":
+            dX = self._buf("dXh", (M, B, D), bf)
+            for i in range(M):
+                ops.gemm_bf16(dZ1[i], W1h[i], dX[i], M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_BF16)
+            self._dDP(dX, coef, nspec, row0)
+        else:
+            gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
+            gb1, gb2 = self.view("b1", self.grad), self.view("b2", self.grad)
+            gW1.zero_(); gW2.zero_()
+            for i in range(M):
+                # dW = dZ^T . act: both operands are stored [K=B, *] -> MN-major, K = batch, stream-K
+                ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+                ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+                ops.colsum(dZ2[i], out=gb2[i])
+                ops.colsum(dZ1[i], out=gb1[i])
+        return res
+
+    # ---- public steps ---------------------------------------------------------------------------
+    def train_step(self, blocks, labels, row0=0, global_batch=None, grad_hook=None):
+        """One reference step (past_acc.py:198-212) for every model.  `blocks`: list of [B,Di]
+        (shared by all models) or [M,B,Di]; labels int64 [B] / [B,1] (or [M,B]).
+        `grad_hook(tensor)` is called on each gradient buffer before its Adam step (data-parallel
+        all-reduce).  Returns per-model stats of pass 2: dict(loss[M], acc[M])."""
+        labels = self._labels(labels)
+        blocks = [b.contiguous() for b in blocks]
+        self._pass(blocks, labels, hard=False, mode="dp", row0=row0, global_batch=global_batch)
+        if grad_hook is not None:
+            grad_hook(self.dDP)
+        self.t_dp += 1
+        ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
+        res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch)
+        if grad_hook is not None:
+            grad_hook(self.grad)
+        self.t_model += 1
+        ops.adam_step(self.flat, self.grad, self.m, self.v, self.t_model, self.lr, self.betas, self.adam_eps,
+                      bf16_shadow=self.shadow)
+        st = res["stats"].view(self.M, 4)
+        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1])
+
+    @torch.no_grad()
+    def eval_step(self, blocks, labels, row0=0):
+        """past_acc.py:218-228: hard=True, noise still sampled.  Returns dict(loss, acc, pred, logits)."""
+        labels = self._labels(labels)
+        res = self._pass([b.contiguous() for b in blocks], labels, hard=True, mode="eval", row0=row0)
+        st = res["stats"].view(self.M, 4)
+        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], pred=res["pred"], logits=res["logits"])

@@ -1,0 +1,286 @@
+"""Tensor-level wrappers over the C ABI: validate torch tensors, pass raw device pointers and
+the current CUDA stream.  No arithmetic happens here and nothing falls back to torch ops."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t) -> int:
+    if t.dtype == torch.float32:
+        return L.DT_F32
+    if t.dtype == torch.bfloat16:
+        return L.DT_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the pgfuse kernels have no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError(f"{name} must be contiguous in its last dimension")
+    return t
+
+
+class Workspace:
+    """Grow-only scratch buffer (caller-owned scratch of the C ABI)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        n = max(4, (nbytes + 3) // 4)
+        if self.buf is None or self.buf.numel() < n or self.buf.device != device:
+            self.buf = torch.empty(n, dtype=torch.float32, device=device)
+        return self.buf
+
+
+_ws = {}
+
+
+def workspace(tag: str) -> Workspace:
+    return _ws.setdefault(tag, Workspace())
+
+
+# --------------------------------------------------------------------------------------------
+def dp_coeffs(DP: torch.Tensor, exp_eps: float, fixed: bool = True):
+    """(w, eps_hat, deps_dDP), each [D].  models.py:73,75."""
+    _chk(DP, torch.float32, "DP")
+    D = DP.numel()
+    out = torch.empty(3, D, dtype=torch.float32, device=DP.device)
+    L.call("pgf_dp_coeffs", DP.data_ptr(), float(exp_eps), int(fixed), D, out[0].data_ptr(), out[1].data_ptr(),
+           out[2].data_ptr(), _stream())
+    return out[0], out[1], out[2]
+
+
+def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed=0, offset=0, row0=0, tau=1.0,
+                     hard=True, want_gate=False, out_dtype=torch.float32, out=None, want_gate_idx=False,
+                     want_minmax=False):
+    """models.py:69-79 in one kernel.  Returns (out[B,D], gate_idx|None, row_min|None, row_max|None)."""
+    blocks = [_chk(b, torch.float32, "feature block") for b in blocks]
+    if not 1 <= len(blocks) <= 3:
+        raise ValueError("1 to 3 feature blocks expected")
+    B = blocks[0].shape[0]
+    dims = [b.shape[1] for b in blocks]
+    D = sum(dims)
+    dev = blocks[0].device
+    if out is None:
+        out = torch.empty(B, D, dtype=out_dtype, device=dev)
+    gate_idx = torch.empty(B, D, dtype=torch.uint8, device=dev) if (want_gate and want_gate_idx) else None
+    rmin = torch.empty(B, dtype=torch.float32, device=dev) if want_minmax else None
+    rmax = torch.empty(B, dtype=torch.float32, device=dev) if want_minmax else None
+    bl = blocks + [None] * (3 - len(blocks))
+    args = []
+    for b in bl:
+        args += [_ptr(b), 0 if b is None else b.shape[1], 0 if b is None else b.stride(0)]
+    if lap is not None:
+        _chk(lap, torch.float32, "lap")
+        assert lap.is_contiguous() and lap.numel() == B * D
+    if gum is not None:
+        _chk(gum, torch.float32, "gum")
+        assert gum.is_contiguous() and gum.numel() == 2 * B * D
+    L.call("pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
+           int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
+           out.stride(0), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), _stream())
+    return out, gate_idx, rmin, rmax
+
+
+def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0, row0=0, out=None, accumulate=False):
+    """dDP[D] = deps_dDP * sum_b dF * noise.  Autograd of models.py:75-76."""
+    _chk(dF, None, "dF")
+    B, D = dF.shape
+    if out is None:
+        out = torch.empty(D, dtype=torch.float32, device=dF.device)
+    nbytes = L.query("pgf_perturb_gate_bwd_dp_workspace", B, D)
+    ws = workspace("perturb_bwd").get(nbytes, dF.device)
+    L.call("pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(0), B, D, noise_mode, _ptr(lap), int(seed),
+           int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), ws.data_ptr(), ws.numel() * 4, out.data_ptr(),
+           int(accumulate), _stream())
+    return out
+
+
+def minmax_norm_bwd(blocks, dn):
+    """Gradient wrt the raw feature blocks through models.py:70-72."""
+    blocks = [_chk(b, torch.float32, "feature block") for b in blocks]
+    _chk(dn, None, "dn")
+    B = blocks[0].shape[0]
+    dxs = [torch.empty_like(b) for b in blocks]
+    bl = blocks + [None] * (3 - len(blocks))
+    dl = dxs + [None] * (3 - len(dxs))
+    args = []
+    for b in bl:
+        args += [_ptr(b), 0 if b is None else b.shape[1], 0 if b is None else b.stride(0)]
+    dargs = []
+    for d in dl:
+        dargs += [_ptr(d), 0 if d is None else d.stride(0)]
+    L.call("pgf_minmax_norm_bwd", *args, dn.data_ptr(), _dt(dn), dn.stride(0), B, *dargs, _stream())
+    return dxs
+
+
+# --------------------------------------------------------------------------------------------
+def _grouped(t, nd):
+    """(tensor, n_models, model_stride) for a [*, ...] or [n_models, *, ...] tensor."""
+    if t.dim() == nd:
+        return 1, 0
+    assert t.dim() == nd + 1, f"expected {nd} or {nd + 1} dims, got {t.dim()}"
+    return t.shape[0], t.stride(0)
+
+
+def linear_fwd(X, W, bias, act=L.ACT_NONE, out=None):
+    """Y = act(X W^T + bias); X [B,K] or [m,B,K], W [N,K] or [m,N,K] (fp32, CUDA-core path)."""
+    _chk(X, torch.float32, "X"); _chk(W, torch.float32, "W")
+    nm, sW = _grouped(W, 2)
+    nx, sX = _grouped(X, 2)
+    n_models = max(nm, nx)
+    B, K = X.shape[-2:]
+    N = W.shape[-2]
+    assert W.shape[-1] == K and W.stride(-2) == K, "W must be dense [N,K]"
+    if out is None:
+        out = torch.empty((*X.shape[:-1], N) if nx > 1 or nm == 1 else (nm, B, N), dtype=torch.float32, device=X.device)
+    sY = out.stride(0) if out.dim() == 3 else 0
+    sb = 0 if bias is None or bias.dim() == 1 else bias.stride(0)
+    L.call("pgf_linear_fwd", X.data_ptr(), X.stride(-2), sX, W.data_ptr(), sW, _ptr(bias), sb, out.data_ptr(),
+           out.stride(-2), sY, B, N, K, act, n_models, _stream())
+    return out
+
+
+def linear_bwd_dx(dY, W, mask_src=None, mask_mode=L.ACT_RELU, out=None):
+    """dX = dY W, times act'(mask_src) when given (RELU: src>0, TANH: 1-src^2)."""
+    _chk(dY, torch.float32, "dY"); _chk(W, torch.float32, "W")
+    nm, sW = _grouped(W, 2)
+    ny, sdY = _grouped(dY, 2)
+    n_models = max(nm, ny)
+    B, N = dY.shape[-2:]
+    K = W.shape[-1]
+    if out is None:
+        out = torch.empty((*dY.shape[:-1], K), dtype=torch.float32, device=dY.device)
+    sdX = out.stride(0) if out.dim() == 3 else 0
+    nbytes = L.query("pgf_linear_bwd_dx_workspace", B, N, K, n_models)
+    ws = workspace("linear_dx").get(nbytes, dY.device)
+    ld_mask = 0 if mask_src is None else mask_src.stride(-2)
+    s_mask = 0 if mask_src is None or mask_src.dim() == 2 else mask_src.stride(0)
+    L.call("pgf_linear_bwd_dx", dY.data_ptr(), dY.stride(-2), sdY, W.data_ptr(), sW, _ptr(mask_src), mask_mode, ld_mask, s_mask,
+           out.data_ptr(), out.stride(-2), sdX, B, N, K, n_models, ws.data_ptr(), ws.numel() * 4, _stream())
+    return out
+
+
+def linear_bwd_dw(dY, X, dW=None, db=None, want_db=True, accumulate=False):
+    """dW = dY^T X, db = colsum(dY)."""
+    _chk(dY, torch.float32, "dY"); _chk(X, torch.float32, "X")
+    ny, sdY = _grouped(dY, 2)
+    nx, sX = _grouped(X, 2)
+    n_models = max(nx, ny)
+    B, N = dY.shape[-2:]
+    K = X.shape[-1]
+    lead = (n_models,) if (dY.dim() == 3 or X.dim() == 3) else ()
+    if dW is None:
+        dW = torch.empty((*lead, N, K), dtype=torch.float32, device=dY.device)
+    if db is None and want_db:
+        db = torch.empty((*lead, N), dtype=torch.float32, device=dY.device)
+    sdW = dW.stride(0) if dW.dim() == 3 else 0
+    sdb = 0 if db is None or db.dim() == 1 else db.stride(0)
+    L.call("pgf_linear_bwd_dw", dY.data_ptr(), dY.stride(-2), sdY, X.data_ptr(), X.stride(-2), sX, dW.data_ptr(), sdW,
+           _ptr(db), sdb, B, N, K, int(accumulate), n_models, _stream())
+    return dW, db
+
+
+# optional per-launch timing of the GEMMs (bench.py roofline): list of (tag, start_event, end_event)
+GEMM_TIMING = None
+
+
+def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, bias=None, aux=None, stream_k=False):
+    """C[M,N] = A . B^T on tcgen05 (bf16 in, fp32 accumulate in TMEM) with a fused epilogue."""
+    _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _chk(C, None, "C")
+    if GEMM_TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k)
+        e1.record()
+        GEMM_TIMING.append(((M, N, K, int(a_mn), int(b_mn), epi), e0, e1))
+        return C
+    return _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k)
+
+
+def _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k):
+    L.call("pgf_gemm_bf16", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), C.data_ptr(),
+           C.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), 0 if aux is None else aux.stride(0), int(stream_k), _stream())
+    return C
+
+
+def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=True, want_logits=True, want_pred=True,
+           dz_dtype=None, dz=None, dWc=None, dbc=None):
+    """classifier + mean-CE + accuracy (+ backward).  Returns dict(logits, pred, stats, dz, dWc, dbc)."""
+    _chk(h, None, "h"); _chk(Wc, torch.float32, "Wc"); _chk(bc, torch.float32, "bc")
+    nh, sh = _grouped(h, 2)
+    nw, sWc = _grouped(Wc, 2)
+    n_models = max(nh, nw)
+    B, H = h.shape[-2:]
+    dev = h.device
+    lead = (n_models,) if (h.dim() == 3 or Wc.dim() == 3) else ()
+    if Wc.shape[-2] != 2:
+        raise NotImplementedError("the reference head has 2 classes (nn.Linear(768, 2), models.py:52)")
+    sbc = 0 if bc.dim() == 1 else bc.stride(0)
+    slab = 0
+    if labels is not None:
+        _chk(labels, torch.int64, "labels")
+        slab = labels.stride(0) if labels.dim() == 2 else 0
+    logits = torch.empty((*lead, B, 2), dtype=torch.float32, device=dev) if want_logits else None
+    pred = torch.empty((*lead, B), dtype=torch.int64, device=dev) if want_pred else None
+    stats = torch.empty((*lead, 4), dtype=torch.float32, device=dev)
+    dWc = dbc = None
+    if backward:
+        if dz is None:
+            dz = torch.empty(h.shape, dtype=dz_dtype or h.dtype, device=dev)
+        if dWc is None:
+            dWc = torch.empty((*lead, 2, H), dtype=torch.float32, device=dev)
+        if dbc is None:
+            dbc = torch.empty((*lead, 2), dtype=torch.float32, device=dev)
+    nbytes = L.query("pgf_cls_ce_workspace", B, H, n_models)
+    ws = workspace("cls_ce").get(nbytes, dev)
+    g3 = lambda t: 0 if t is None or t.dim() < len(lead) + 1 or not lead else t.stride(0)
+    L.call("pgf_cls_ce", h.data_ptr(), _dt(h), h.stride(-2), sh, Wc.data_ptr(), sWc, bc.data_ptr(), sbc, _ptr(labels), slab,
+           B, H, n_models, float(loss_scale), float(grad_scale), int(bool(backward)), int(bool(through_tanh)),
+           _ptr(logits), g3(logits), _ptr(pred), g3(pred), stats.data_ptr(), _ptr(dz), 0 if dz is None else _dt(dz),
+           0 if dz is None else dz.stride(-2), 0 if dz is None or dz.dim() == 2 else dz.stride(0), _ptr(dWc), g3(dWc),
+           _ptr(dbc), g3(dbc), ws.data_ptr(), ws.numel() * 4, _stream())
+    return dict(logits=logits, pred=pred, stats=stats, dz=dz, dWc=dWc, dbc=dbc)
+
+
+def adam_step(p, g, m, v, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, bf16_shadow=None):
+    """torch.optim.Adam single step over flat fp32 buffers (past_acc.py:157-160,203,212)."""
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk(t, torch.float32, n)
+        assert t.is_contiguous()
+    L.call("pgf_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(bf16_shadow), p.numel(), int(step),
+           float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _stream())
+
+
+def cast_bf16(src, dst=None):
+    _chk(src, torch.float32, "src")
+    assert src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    L.call("pgf_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    return dst
+
+
+def colsum(x, out=None):
+    _chk(x, None, "x")
+    B, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+    nbytes = L.query("pgf_colsum_workspace", B, N)
+    ws = workspace("colsum").get(nbytes, x.device)
+    L.call("pgf_colsum", x.data_ptr(), _dt(x), x.stride(0), B, N, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
+    return out

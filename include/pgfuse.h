@@ -1,0 +1,158 @@
+/* pgfuse.h -- C ABI of libpgfuse.so: the B200 (sm_100a) kernels behind the privatised fusion head
+ * of Rachfu/EEG-multimodal.
+ *
+ * The reference exposes this path only as Python nn.Module code (there is no native layer to
+ * bind), so every entry point below replaces a span of torch ops; the span is cited per function
+ * (paths relative to the reference checkout).  A reference-side binding is a ctypes stub, shown
+ * in INTEGRATION.md; eeg_multimodal_b200/_lib.py is that stub for this repo.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pgf_last_error() gives the
+ *     thread-local message.  Nothing here allocates caller-visible memory or synchronises:
+ *     all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - all pointers are DEVICE pointers unless the name says host; row-major; `ld*` are row
+ *     strides in ELEMENTS; fp32 unless `*_dtype` says otherwise (PGF_DT_F32=0, PGF_DT_BF16=1).
+ *   - "grouped" functions take `n_models` and per-operand model strides `s*` (elements between
+ *     consecutive models; 0 = shared) so an eps x seed sweep is one launch.
+ *   - scratch space is caller-owned: query the size with the matching *_workspace() call.
+ */
+#ifndef PGFUSE_H_
+#define PGFUSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGF_DT_F32 0
+#define PGF_DT_BF16 1
+
+#define PGF_NOISE_INJECTED 0 /* caller supplies Laplace [B,D] and Gumbel [2,B,D] tensors (parity) */
+#define PGF_NOISE_PHILOX 1   /* counter-based Philox4x32-10 in-kernel (production)               */
+#define PGF_NOISE_NONE 2     /* non-private ConcatModel: normalise + concat only (model.py:53-64) */
+
+#define PGF_ACT_NONE 0
+#define PGF_ACT_RELU 1
+#define PGF_ACT_TANH 2
+
+#define PGF_EPI_STORE_BF16 0
+#define PGF_EPI_BIAS_RELU_BF16 1
+#define PGF_EPI_BIAS_TANH_BF16 2
+#define PGF_EPI_RELUMASK_BF16 3
+#define PGF_EPI_ATOMIC_F32 4
+#define PGF_EPI_STORE_F32 5
+#define PGF_EPI_BIAS_F32 6
+
+int pgf_version(void);
+const char* pgf_last_error(void);
+int pgf_num_sms(void);
+
+/* ---- (a3,a4) per-column privacy coefficients -------------------------------------------------
+ * replaces: w = F.sigmoid(self.DP); eps_hat = 1/(((eps.exp()-w)/(1-w)).log())
+ *           python/src/custom_models/models.py:73,75 (== past_acc.py:130,132); the unfixed form
+ *           (fixed_formula=0) is model.py:57.  `exp_eps` is e^eps already rounded to fp32 by the
+ *           host, exactly the scalar that enters `(eps.exp() - w)`.
+ * outputs (each [D], any may be NULL): w, eps_hat, deps_dDP = d eps_hat / d DP.              */
+int pgf_dp_coeffs(const float* DP, float exp_eps, int fixed_formula, int D, float* w, float* eps_hat,
+                  float* deps_dDP, void* stream);
+
+/* ---- (a1,a2,a5,a6,a7) fused concat + row min-max normalise + Laplace perturbation + gate -----
+ * replaces: models.py:69-79 (== past_acc.py:120-136): torch.cat, torch.min/max, (x-min)/(max-min),
+ *           Laplace.sample on the host + .to(device), feature + noise*eps_hat, F.gumbel_softmax over
+ *           the stacked (w, 1-w) planes, (feature*mask).sum(0).
+ * x0/x1/x2: up to three feature blocks [B,d_i] (d_i % 4 == 0, d2 may be 0 with x2 NULL); D = sum d_i.
+ * noise_mode INJECTED: lap [B,D], gum [2,B,D] (gum may be NULL -> gate skipped);
+ *            PHILOX:   seed/offset/row0 key the counter (row0 = global index of row 0, so the
+ *                      noise does not depend on how a batch is split across GPUs);
+ *            NONE:     out = normalised features.
+ * want_gate: evaluate the Gumbel gate (mask applied faithfully in INJECTED mode; in PHILOX mode the
+ *            two mask planes sum to one so only the gate index is a real output).
+ * out: [B,D] fp32 or bf16 (ld_out); gate_idx [B,D] uint8, row_min/row_max [B]: optional.       */
+int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1,
+                         const float* x2, int d2, long long ld2, const float* w, const float* eps_hat, int B,
+                         int noise_mode, const float* lap, const float* gum, unsigned long long seed,
+                         unsigned int offset, unsigned long long row0, float tau, int hard, int want_gate,
+                         void* out, int out_dtype, long long ld_out, unsigned char* gate_idx, float* row_min,
+                         float* row_max, void* stream);
+
+/* ---- (a11) dL/dDP through the perturbation ----------------------------------------------------
+ * replaces: autograd through models.py:75-76: dDP[d] = deps_dDP[d] * sum_b dF[b,d] * noise[b,d]
+ *           (the gate's own contribution is zero in exact arithmetic).
+ * dF: gradient wrt the gated feature [B,D] fp32/bf16.  accumulate!=0 adds into dDP.             */
+size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D);
+int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, int B, int D, int noise_mode,
+                            const float* lap, unsigned long long seed, unsigned int offset,
+                            unsigned long long row0, const float* deps_dDP, float* workspace,
+                            size_t workspace_bytes, float* dDP, int accumulate, void* stream);
+
+/* ---- (a11) gradient wrt the raw feature blocks through the min-max normalisation -------------
+ * replaces: autograd through models.py:70-72 (only needed when the encoders are trained).
+ * dn: gradient wrt the normalised (== perturbed == gated) feature [B,D].                        */
+int pgf_minmax_norm_bwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1,
+                        const float* x2, int d2, long long ld2, const void* dn, int dn_dtype, long long ld_dn,
+                        int B, float* dx0, long long ldd0, float* dx1, long long ldd1, float* dx2,
+                        long long ldd2, void* stream);
+
+/* ---- (a8) fusion MLP, fp32 CUDA-core path (small batch, weight-streaming bound), grouped -----
+ * replaces: nn.Linear(+ReLU/Tanh) of fc_layers and autograd, models.py:46-51,80.
+ * W is torch layout [N,K] (out,in).  fwd: Y = act(X W^T + bias).
+ * dx:  dX = dY W, optionally times the derivative of the activation that produced mask_src
+ *      (mask_mode PGF_ACT_RELU: (mask_src > 0); PGF_ACT_TANH: (1 - mask_src^2)).
+ * dw:  dW = dY^T X (+= if accumulate), db = colsum(dY) (db may be NULL).                        */
+int pgf_linear_fwd(const float* X, long long ldx, long long sX, const float* W, long long sW, const float* bias,
+                   long long sb, float* Y, long long ldy, long long sY, int B, int N, int K, int act,
+                   int n_models, void* stream);
+size_t pgf_linear_bwd_dx_workspace(int B, int N, int K, int n_models);
+int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float* W, long long sW,
+                      const float* mask_src, int mask_mode, long long ld_mask, long long s_mask, float* dX, long long ldx,
+                      long long sdX, int B, int N, int K, int n_models, float* workspace,
+                      size_t workspace_bytes, void* stream);
+int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX,
+                      float* dW, long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate,
+                      int n_models, void* stream);
+
+/* ---- (a8) fusion MLP, tcgen05 tensor-core path (large batch) ----------------------------------
+ * replaces: the same nn.Linear GEMMs when the batch is a real dense contraction.
+ * C[M,N] = A[M,K] . B[N,K]^T, bf16 operands, fp32 accumulation in TMEM, fused epilogue `epi`.
+ * a_mn / b_mn != 0: that operand is stored transposed ([K,M] / [K,N] row-major), as the
+ * weight-gradient GEMMs need.  stream_k != 0 (with PGF_EPI_ATOMIC_F32, C zeroed by the caller)
+ * splits K across CTAs.  bias [N] fp32; aux [M,N] bf16 (ReLU mask source).                      */
+int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C,
+                  long long ldc, int M, int N, int K, int epi, const float* bias, const void* aux,
+                  long long ld_aux, int stream_k, void* stream);
+
+/* ---- (a9,a10,a11) classifier + softmax cross-entropy + accuracy, fwd (+bwd), grouped ---------
+ * replaces: self.classifier (models.py:81) and cal_loss (base_train.py:59-65 == past_acc.py:71-77)
+ *           and their autograd, including the gradient through the Tanh in front of the classifier.
+ * h [B,H] (fp32/bf16) is the Tanh output; labels int64 [B] (slabels = 0 shares them);
+ * outputs: logits [B,2], pred int64 [B] (optional); stats[model*4 + {0..3}] =
+ *          {loss_sum*loss_scale, n_correct, n_correct*loss_scale, B};
+ * backward!=0: dz [B,H] = (dlogits . Wc) * (1-h^2 if through_tanh), dWc [2,H], dbc [2], with
+ *          dlogits = (softmax - onehot) * grad_scale.                                            */
+size_t pgf_cls_ce_workspace(int B, int H, int n_models);
+int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const float* Wc, long long sWc,
+               const float* bc, long long sbc, const long long* labels, long long slabels, int B, int H,
+               int n_models, float loss_scale, float grad_scale, int backward, int through_tanh, float* logits,
+               long long slogits, long long* pred, long long spred, float* stats, void* dz, int dz_dtype,
+               long long lddz, long long sdz, float* dWc, long long sdWc, float* dbc, long long sdbc,
+               float* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (a12,f1) Adam over a flat fp32 buffer ----------------------------------------------------
+ * replaces: torch.optim.Adam(...).step() for either parameter group (past_acc.py:155-160,203,212),
+ *           torch defaults; `step` is the 1-based step count.  `bf16_shadow` (optional) receives a
+ *           bf16 copy of the updated parameters for the tensor-core path.                        */
+int pgf_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---- helpers for the tensor-core path ---------------------------------------------------------*/
+int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+size_t pgf_colsum_workspace(int B, int N);
+int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out, float* workspace,
+               size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGFUSE_H_ */

@@ -1,0 +1,377 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ops.* are 1:1 ctypes calls).
+
+Checker = oracle/ (CPU restatement of the reference) on the same seeded inputs.  Bars
+(BASELINE.json north_star): fp32 outputs and gradients within 1e-5 relative, bf16-GEMM mode
+within 2e-2, gate indices and argmax predictions bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_dp
+from oracle import head_oracle as ho
+from oracle import philox_ref
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from eeg_multimodal_b200 import _lib
+
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_blocks(B, dims, seed, dist="uniform"):
+    g = torch.Generator().manual_seed(seed)
+    if dist == "uniform":
+        return [torch.rand(B, d, generator=g) for d in dims]
+    return [torch.randn(B, d, generator=g) * 0.5 for d in dims]
+
+
+def oracle_perturb(blocks, DP, eps, lap, gum, hard, fixed=True, tau=1.0):
+    p = ho.HeadParams(*(torch.zeros(1),) * 6, DP.view(1, -1))
+    eps_t = ho.eps_tensor(eps)
+    feature = ho.minmax_normalise(torch.cat(blocks, 1))
+    w = torch.sigmoid(p.DP)
+    eh = ho.eps_hat_of(w, eps_t, fixed)
+    fp = feature + lap * eh
+    if gum is None:
+        return fp, None, feature
+    mask, idx = ho.gumbel_mask(w, fp.shape[0], gum, hard, tau)
+    return (fp * mask).sum(0), idx, feature
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (a) forward
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 2, 8, 601])
+@pytest.mark.parametrize("dims", [(768, 768, 768), (2048, 512), (64,), (1024, 2048, 1024)])
+@pytest.mark.parametrize("hard", [True, False])
+def test_perturb_gate_injected_matches_oracle(dev, golden, B, dims, hard):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    D = sum(dims)
+    blocks = make_blocks(B, dims, 100 + B, "normal")
+    lap, gum = ho.replay_reference_draws(7 + B, B, D)
+    DP = torch.from_numpy(golden_dp(golden, "wvalues"))[:D] if D <= 2304 else torch.randn(D, generator=torch.Generator().manual_seed(1)) * 0.1
+    for eps in (0.1, 1.0, 8.0):
+        ref, ref_idx, ref_norm = oracle_perturb(blocks, DP, eps, lap, gum, hard)
+        w, eh, _ = ops.dp_coeffs(DP.to(dev), ho.exp_eps_f32(eps))
+        out, idx, rmin, rmax = ops.perturb_gate_fwd([b.to(dev) for b in blocks], w, eh, noise_mode=L.NOISE_INJECTED,
+                                                    lap=lap.to(dev), gum=gum.to(dev), hard=hard, want_gate=True,
+                                                    want_gate_idx=True, want_minmax=True)
+        torch.cuda.synchronize()
+        assert rel_err(out, ref) < RTOL, (eps, rel_err(out, ref))
+        cat = torch.cat(blocks, 1)
+        assert torch.equal(rmin.cpu(), cat.min(1)[0]) and torch.equal(rmax.cpu(), cat.max(1)[0])
+        # gate index: bit-exact, except where the two logits are within a few ulp (sigmoid/exp ulp differences)
+        wcpu = torch.sigmoid(DP)
+        z0, z1 = wcpu + gum[0], (1 - wcpu) + gum[1]
+        near_tie = (z0 - z1).abs() < 1e-5
+        mism = (idx.cpu().long() != ref_idx) & ~near_tie
+        assert int(mism.sum()) == 0
+        assert int(near_tie.sum()) < 1e-3 * near_tie.numel() + 2
+
+
+def test_perturb_gate_hard_is_identity_on_device(dev):
+    """models.py:77-79 known answer: with hard=True the gated value equals the perturbed value bit for bit."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    B, dims = 8, (768, 768, 768)
+    blocks = [b.to(dev) for b in make_blocks(B, dims, 3)]
+    lap, gum = ho.replay_reference_draws(5, B, sum(dims))
+    w, eh, _ = ops.dp_coeffs(torch.zeros(sum(dims), device=dev), ho.exp_eps_f32(1.0))
+    a, _, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_INJECTED, lap=lap.to(dev), gum=gum.to(dev), hard=True, want_gate=True)
+    b, _, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_INJECTED, lap=lap.to(dev), gum=None, hard=True, want_gate=False)
+    assert torch.equal(a, b)
+    # DP = 0 -> w = 0.5 exactly: gate index must be bit-exact with the oracle, no tolerance
+    _, ref_idx, _ = oracle_perturb([x.cpu() for x in blocks], torch.zeros(sum(dims)), 1.0, lap, gum, True)
+    _, idx, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_INJECTED, lap=lap.to(dev), gum=gum.to(dev), hard=True,
+                                        want_gate=True, want_gate_idx=True)
+    assert torch.equal(idx.cpu().long(), ref_idx)
+
+
+@pytest.mark.parametrize("dims", [(768, 768, 768), (2048, 512)])
+def test_perturb_gate_philox_matches_oracle_noise(dev, dims):
+    """Philox mode == oracle fed with the numpy restatement of the same counters."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    B, D, seed, offset, row0 = 37, sum(dims), 980616, 5, 1000
+    blocks = make_blocks(B, dims, 11)
+    DP = torch.randn(D, generator=torch.Generator().manual_seed(2)) * 0.2
+    lap = torch.from_numpy(philox_ref.laplace(seed, offset, row0, B, D))
+    gum = torch.from_numpy(philox_ref.gumbel(seed, offset, row0, B, D))
+    ref, ref_idx, _ = oracle_perturb(blocks, DP, 1.0, lap, gum, True)
+    w, eh, _ = ops.dp_coeffs(DP.to(dev), ho.exp_eps_f32(1.0))
+    dblocks = [b.to(dev) for b in blocks]
+    out, idx, _, _ = ops.perturb_gate_fwd(dblocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=seed, offset=offset, row0=row0,
+                                          hard=True, want_gate=True, want_gate_idx=True)
+    assert rel_err(out, ref) < RTOL
+    wcpu = torch.sigmoid(DP)
+    near_tie = ((wcpu + gum[0]) - ((1 - wcpu) + gum[1])).abs() < 1e-4
+    assert int(((idx.cpu().long() != ref_idx) & ~near_tie).sum()) == 0
+    # partition invariance: the second half computed alone with row0 shifted is bit-identical
+    h = B // 2
+    part, _, _, _ = ops.perturb_gate_fwd([b[h:].contiguous() for b in dblocks], w, eh, noise_mode=L.NOISE_PHILOX, seed=seed,
+                                         offset=offset, row0=row0 + h, hard=True)
+    assert torch.equal(part, out[h:])
+    # a different offset gives fresh noise; bf16 output is the rounded fp32 output
+    other, _, _, _ = ops.perturb_gate_fwd(dblocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=seed, offset=offset + 1, row0=row0, hard=True)
+    assert not torch.equal(other, out)
+    ob, _, _, _ = ops.perturb_gate_fwd(dblocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=seed, offset=offset, row0=row0, hard=True,
+                                       out_dtype=torch.bfloat16)
+    assert torch.equal(ob, out.to(torch.bfloat16))
+
+
+def test_perturb_gate_edge_cases(dev):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    dims = (64, 64)
+    w, eh, _ = ops.dp_coeffs(torch.zeros(128, device=dev), ho.exp_eps_f32(1.0))
+    x = [torch.rand(4, 64, device=dev), torch.rand(4, 64, device=dev)]
+    x[0][1] = 0.25
+    x[1][1] = 0.25            # constant row: max == min -> NaN like the reference (no epsilon guard)
+    x[0][2, 5] = float("nan")  # NaN input poisons its row only
+    out, _, _, _ = ops.perturb_gate_fwd(x, w, eh, noise_mode=L.NOISE_PHILOX, seed=1)
+    assert torch.isnan(out[1]).all() and torch.isnan(out[2]).all()
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[3]).all()
+    # non-private path: range exactly [0, 1]
+    n, _, _, _ = ops.perturb_gate_fwd([x[0][[0, 3]].contiguous(), x[1][[0, 3]].contiguous()], None, None, noise_mode=L.NOISE_NONE)
+    assert float(n.min()) == 0.0 and float(n.max()) == 1.0
+    ref = ho.minmax_normalise(torch.cat([x[0][[0, 3]].cpu(), x[1][[0, 3]].cpu()], 1))
+    assert torch.equal(n.cpu(), ref)
+    # empty batch is a no-op; ragged widths are rejected
+    e, _, _, _ = ops.perturb_gate_fwd([torch.empty(0, 64, device=dev)], w[:64].contiguous(), eh[:64].contiguous(), noise_mode=L.NOISE_PHILOX)
+    assert e.shape == (0, 64)
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        ops.perturb_gate_fwd([torch.rand(2, 66, device=dev)], w, eh, noise_mode=L.NOISE_PHILOX)
+    with pytest.raises(RuntimeError, match="4096"):
+        ops.perturb_gate_fwd([torch.rand(2, 4100, device=dev)], w, eh, noise_mode=L.NOISE_NONE)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (a) backward
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixed", [True, False])
+@pytest.mark.parametrize("B", [1, 8, 601])
+def test_dDP_matches_autograd(dev, golden, B, fixed):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    D = 2304
+    blocks = make_blocks(B, (768, 768, 768), 5)
+    lap, gum = ho.replay_reference_draws(3, B, D)
+    dF = torch.randn(B, D, generator=torch.Generator().manual_seed(9)) * 1e-3
+    for eps in (0.1, 1.0, 8.0):
+        DP = torch.from_numpy(golden_dp(golden, "wvalues")).clone().requires_grad_(True)
+        w = torch.sigmoid(DP.view(1, -1))
+        fp = ho.minmax_normalise(torch.cat(blocks, 1)) + lap * ho.eps_hat_of(w, ho.eps_tensor(eps), fixed)
+        (fp * dF).sum().backward()
+        _, _, deps = ops.dp_coeffs(DP.detach().to(dev), ho.exp_eps_f32(eps), fixed)
+        got = ops.perturb_gate_bwd_dp(dF.to(dev), deps, noise_mode=L.NOISE_INJECTED, lap=lap.to(dev))
+        assert rel_err(got, DP.grad) < RTOL
+        got16 = ops.perturb_gate_bwd_dp(dF.to(dev).to(torch.bfloat16), deps, noise_mode=L.NOISE_INJECTED, lap=lap.to(dev))
+        assert rel_err(got16, DP.grad) < 2e-2
+
+
+def test_dDP_philox_regenerates_forward_noise(dev):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    B, D, seed, offset, row0 = 200, 2560, 42, 9, 77
+    dF = torch.randn(B, D, generator=torch.Generator().manual_seed(1)).to(dev)
+    _, _, deps = ops.dp_coeffs(torch.zeros(D, device=dev), ho.exp_eps_f32(1.0))
+    lap = torch.from_numpy(philox_ref.laplace(seed, offset, row0, B, D)).to(dev)
+    a = ops.perturb_gate_bwd_dp(dF, deps, noise_mode=L.NOISE_PHILOX, seed=seed, offset=offset, row0=row0)
+    b = ops.perturb_gate_bwd_dp(dF, deps, noise_mode=L.NOISE_INJECTED, lap=lap)
+    assert rel_err(a, b) < RTOL
+    ref = (dF.double() * lap.double()).sum(0) * deps.double()
+    assert rel_err(a, ref) < RTOL
+
+
+def test_minmax_norm_bwd_matches_autograd(dev):
+    from eeg_multimodal_b200 import ops
+
+    for dims in ((768, 768, 768), (2048, 512)):
+        blocks = [b.requires_grad_(True) for b in make_blocks(9, dims, 21, "normal")]
+        dn = torch.randn(9, sum(dims), generator=torch.Generator().manual_seed(4))
+        (ho.minmax_normalise(torch.cat(blocks, 1)) * dn).sum().backward()
+        got = ops.minmax_norm_bwd([b.detach().to(dev) for b in blocks], dn.to(dev))
+        for g, b in zip(got, blocks):
+            assert rel_err(g, b.grad) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (b) fp32 CUDA-core path (grouped)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_models,B,N,K", [(1, 8, 2304, 2304), (3, 8, 768, 2304), (2, 5, 2, 768), (1, 19, 260, 512), (48, 8, 768, 768)])
+def test_linear_fp32_grouped(dev, n_models, B, N, K):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    g = torch.Generator().manual_seed(N + K)
+    X = torch.randn(n_models, B, K, generator=g)
+    W = torch.randn(n_models, N, K, generator=g) / K ** 0.5
+    b = torch.randn(n_models, N, generator=g)
+    dY = torch.randn(n_models, B, N, generator=g)
+    Xd, Wd, bd, dYd = (t.to(dev) for t in (X, W, b, dY))
+    Z = torch.einsum("mbk,mnk->mbn", X.double(), W.double()) + b.double()[:, None]
+    for act, f in ((L.ACT_NONE, lambda z: z), (L.ACT_RELU, torch.relu), (L.ACT_TANH, torch.tanh)):
+        assert rel_err(ops.linear_fwd(Xd, Wd, bd, act), f(Z)) < RTOL
+    dX = torch.einsum("mbn,mnk->mbk", dY.double(), W.double())
+    assert rel_err(ops.linear_bwd_dx(dYd, Wd), dX) < RTOL
+    assert rel_err(ops.linear_bwd_dx(dYd, Wd, mask_src=Xd, mask_mode=L.ACT_RELU), dX * (X > 0)) < RTOL
+    Xt = torch.tanh(Xd)
+    assert rel_err(ops.linear_bwd_dx(dYd, Wd, mask_src=Xt, mask_mode=L.ACT_TANH), dX * (1 - Xt.cpu().double() ** 2)) < RTOL
+    dW, db = ops.linear_bwd_dw(dYd, Xd)
+    assert rel_err(dW, torch.einsum("mbn,mbk->mnk", dY.double(), X.double())) < RTOL
+    assert rel_err(db, dY.double().sum(1)) < RTOL
+    dW2, _ = ops.linear_bwd_dw(dYd, Xd, dW=dW.clone(), db=db.clone(), accumulate=True)
+    assert rel_err(dW2, 2 * torch.einsum("mbn,mbk->mnk", dY.double(), X.double())) < RTOL
+    if n_models == 1:  # ungrouped call shapes
+        assert rel_err(ops.linear_fwd(Xd[0], Wd[0], bd[0], L.ACT_NONE), Z[0]) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (c) classifier + CE + accuracy
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_models,B,H", [(1, 8, 768), (1, 1, 768), (4, 601, 768), (2, 33, 256)])
+def test_cls_ce_matches_cal_loss(dev, n_models, B, H):
+    from eeg_multimodal_b200 import ops
+
+    g = torch.Generator().manual_seed(B + H)
+    for m in range(n_models):
+        pass
+    h = torch.tanh(torch.randn(n_models, B, H, generator=g))
+    Wc = torch.randn(n_models, 2, H, generator=g) / H ** 0.5
+    bc = torch.randn(n_models, 2, generator=g) * 0.1
+    labels = (torch.rand(B, generator=g) < 0.66).long()
+    res = ops.cls_ce(h.to(dev), Wc.to(dev), bc.to(dev), labels.to(dev), loss_scale=1.0 / B, grad_scale=1.0 / B, backward=True)
+    for m in range(n_models):
+        z = torch.atanh(h[m].double().clamp(-0.999999, 0.999999)).float().requires_grad_(True)
+        hh = torch.tanh(z)
+        wc, b_ = Wc[m].clone().requires_grad_(True), bc[m].clone().requires_grad_(True)
+        pred = torch.nn.functional.linear(hh, wc, b_)
+        loss, acc, pid, _ = ho.cal_loss(pred, labels.view(B, 1))
+        loss.backward()
+        assert rel_err(res["logits"][m], pred.detach()) < RTOL
+        assert torch.equal(res["pred"][m].cpu(), pid)                      # argmax: bit-exact
+        st = res["stats"][m].cpu()
+        assert abs(float(st[0]) - float(loss)) < 1e-5 * max(1.0, float(loss))
+        assert float(st[1]) == float((pid == labels).sum()) and abs(float(st[2]) - float(acc)) < 1e-6
+        assert rel_err(res["dWc"][m], wc.grad) < 5e-5 and rel_err(res["dbc"][m], b_.grad) < 5e-5
+        # dz = dL/d(pre-tanh); recomputed tanh from atanh loses a little, so 1e-4 here
+        assert rel_err(res["dz"][m], z.grad) < 2e-4
+    # eval mode: no labels needed for logits/pred; bf16 activations
+    ev = ops.cls_ce(h.to(dev).to(torch.bfloat16), Wc.to(dev), bc.to(dev), None, loss_scale=1.0, grad_scale=1.0, backward=False)
+    ref16 = torch.einsum("mbh,mch->mbc", h.to(torch.bfloat16).double(), Wc.double()) + bc.double()[:, None]
+    assert rel_err(ev["logits"], ref16) < 1e-5
+
+
+def test_adam_matches_torch(dev):
+    from eeg_multimodal_b200 import ops
+
+    n = 10007
+    g0 = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g0)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    pd, m, v = p.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g0) * 10 ** float(torch.randint(-6, 1, (1,), generator=g0))
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step(pd, grad.to(dev), m, v, step, lr=1e-3, bf16_shadow=shadow)
+        assert float((pd.cpu() - ref.detach()).abs().max()) < 2e-7
+    assert torch.equal(shadow, pd.to(torch.bfloat16))
+
+
+def test_colsum_and_cast(dev):
+    from eeg_multimodal_b200 import ops
+
+    x = torch.randn(1000, 768, device=dev)
+    assert rel_err(ops.colsum(x), x.double().sum(0)) < RTOL
+    xb = ops.cast_bf16(x)
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert rel_err(ops.colsum(xb), xb.double().sum(0)) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (b) tcgen05 tensor-core path
+# ------------------------------------------------------------------------------------------------
+def _gemm_ref(A, B, a_mn, b_mn):
+    Am = A.double().cpu().t() if a_mn else A.double().cpu()
+    Bm = B.double().cpu().t() if b_mn else B.double().cpu()
+    return Am @ Bm.t()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (200, 264, 136), (1000, 768, 2304)])
+def test_gemm_bf16_tcgen05_layouts(dev, a_mn, b_mn, M, N, K):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn((K, M) if a_mn else (M, K), generator=g)).to(torch.bfloat16).to(dev)
+    Bm = (torch.randn((K, N) if b_mn else (N, K), generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    ref = _gemm_ref(A, Bm, a_mn, b_mn)
+    C = torch.full((M, N), float("nan"), device=dev)
+    ops.gemm_bf16(A, Bm, C, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, epi=L.EPI_STORE_F32)
+    torch.cuda.synchronize()
+    assert rel_err(C, ref) < 1e-5, rel_err(C, ref)
+    Cs = torch.zeros(M, N, device=dev)
+    ops.gemm_bf16(A, Bm, Cs, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, epi=L.EPI_ATOMIC_F32, stream_k=True)
+    assert rel_err(Cs, ref) < 1e-5, rel_err(Cs, ref)
+
+
+def test_gemm_bf16_epilogues(dev):
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    M, N, K = 520, 768, 512
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    aux = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+    z = _gemm_ref(A, W, False, False)
+    zb = z + bias.double().cpu()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    for epi, ref in ((L.EPI_STORE_BF16, z), (L.EPI_BIAS_RELU_BF16, torch.relu(zb)), (L.EPI_BIAS_TANH_BF16, torch.tanh(zb)),
+                     (L.EPI_RELUMASK_BF16, z * (aux.cpu().double() > 0))):
+        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias, aux=aux)
+        assert rel_err(out, ref) < 6e-3, (epi, rel_err(out, ref))   # bf16 output rounding: 2^-8
+    o32 = torch.empty(M, N, device=dev)
+    ops.gemm_bf16(A, W, o32, M=M, N=N, K=K, epi=L.EPI_BIAS_F32, bias=bias)
+    assert rel_err(o32, zb) < 1e-5
+
+
+def test_gemm_bf16_full_size_freivalds(dev):
+    """BASELINE config-4 shapes (B=65536, D=2560): check C v == A (B^T v) instead of a full oracle."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    Bsz, D, H = 65536, 2560, 768
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.rand(Bsz, D, device=dev, generator=g).to(torch.bfloat16)
+    W1 = ((torch.rand(D, D, device=dev, generator=g) * 2 - 1) / D ** 0.5).to(torch.bfloat16)
+    dZ = (torch.randn(Bsz, H, device=dev, generator=g) * 1e-3).to(torch.bfloat16)
+    v = torch.randn(D, device=dev, generator=g, dtype=torch.float64)
+    # forward GEMM, fp32 out
+    C = torch.empty(Bsz, D, device=dev)
+    ops.gemm_bf16(X, W1, C, M=Bsz, N=D, K=D, epi=L.EPI_STORE_F32)
+    lhs = C.double() @ v
+    rhs = X.double() @ (W1.double().t() @ v)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-5
+    # weight-gradient GEMM (K = batch, both operands MN-major, stream-K + fp32 reductions)
+    dW = torch.zeros(H, D, device=dev)
+    ops.gemm_bf16(dZ, X, dW, M=H, N=D, K=Bsz, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+    lhs = dW.double() @ v
+    rhs = dZ.double().t() @ (X.double() @ v)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-4

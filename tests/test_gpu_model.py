@@ -1,0 +1,220 @@
+"""GPU parity tests of the host-side mirror (ConcatModel / get_model) and of the training
+engine against the reference's golden vectors and the oracle's two-pass trainer."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_fields, golden_dp
+from oracle import head_oracle as ho
+
+pytestmark = pytest.mark.gpu
+D = 2304
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b)).double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def load_params(model, p):
+    sd = {"fc_layers.0.weight": p.W1, "fc_layers.0.bias": p.b1, "fc_layers.2.weight": p.W2, "fc_layers.2.bias": p.b2,
+          "classifier.weight": p.Wc, "classifier.bias": p.bc, "DP": p.DP}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing
+
+
+def test_state_dict_layout_matches_reference(dev):
+    from eeg_multimodal_b200 import ConcatModel
+
+    m = ConcatModel()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert shapes == {"classifier.weight": (2, 768), "classifier.bias": (2,), "DP": (1, 2304),
+                      "fc_layers.0.weight": (2304, 2304), "fc_layers.0.bias": (2304,),
+                      "fc_layers.2.weight": (768, 2304), "fc_layers.2.bias": (768,)}
+    # reference scripts split parameters on the substring 'DP' (train.py:71-72, past_acc.py:155-156)
+    assert [n for n, _ in m.named_parameters() if "DP" in n] == ["DP"]
+    assert sum(p.numel() for p in m.parameters()) == 7084802
+
+
+@pytest.mark.parametrize("idx", range(16))
+def test_model_matches_reference_golden(dev, golden, idx):
+    """Same injected Laplace/Gumbel tensors as the reference run: logits and gradients within 1e-5,
+    argmax predictions and gate indices bit-exact."""
+    from eeg_multimodal_b200 import get_model
+
+    key = str(golden["cases"][idx])
+    kind, eps, hard = case_fields(key)
+    model = get_model(types.SimpleNamespace(data_name="EEG", eps=eps))
+    load_params(model, ho.make_params(D, seed=int(golden["param_seed"]), dp=golden_dp(golden, kind)))
+    x = tuple(torch.from_numpy(golden[k]).to(dev) for k in ("eeg", "act", "cm"))
+    label = torch.from_numpy(golden["label"]).to(dev)
+    model.inject_noise(torch.from_numpy(golden["lap"]).to(dev), torch.from_numpy(golden["gum"]).to(dev))
+    pred = model(x, hard=hard)
+    from eeg_multimodal_b200 import cal_loss
+
+    loss, acc, pred_id, _ = cal_loss(pred, label)
+    loss.backward()
+    assert rel_err(pred, golden[key + "_logits"]) < 1e-5
+    assert abs(float(loss) - float(golden[key + "_loss"])) < 1e-5 * max(1.0, abs(float(golden[key + "_loss"])))
+    assert float(acc) == float(golden[key + "_acc"])
+    np.testing.assert_array_equal(pred_id.cpu().numpy(), golden[key + "_pred"])
+    gi, ref_gi = model.last_gate_index.cpu().numpy(), golden[f"{kind}_gate_index"]
+    if kind == "zero":
+        np.testing.assert_array_equal(gi, ref_gi)                       # w = 0.5 exactly: no tolerance
+    else:
+        assert (gi != ref_gi).mean() < 1e-4                             # sigmoid ulp near ties only
+    fc0, fc2 = model.fc_layers[0], model.fc_layers[2]
+    tol = 3e-5 if eps < 0.05 else 1e-5   # eps=0.01: eps_hat ~ 50, the reference's own fp32 conditioning
+    assert rel_err(model.DP.grad, golden[key + "_dDP"]) < tol
+    assert rel_err(fc0.bias.grad, golden[key + "_db1"]) < tol
+    assert rel_err(fc2.bias.grad, golden[key + "_db2"]) < tol
+    assert rel_err(model.classifier.weight.grad, golden[key + "_dWc"]) < tol
+    assert rel_err(model.classifier.bias.grad, golden[key + "_dbc"]) < tol
+    scale1 = float(fc0.weight.grad.abs().max())
+    assert float((fc0.weight.grad[:4].cpu() - torch.from_numpy(golden[key + "_dW1_rows"])).abs().max()) < tol * scale1
+    scale2 = float(fc2.weight.grad.abs().max())
+    assert float((fc2.weight.grad[:4].cpu() - torch.from_numpy(golden[key + "_dW2_rows"])).abs().max()) < tol * scale2
+    assert rel_err(fc0.weight.grad.sum(0), golden[key + "_dW1_colsum"]) < 1e-4
+    assert rel_err(fc2.weight.grad.sum(0), golden[key + "_dW2_colsum"]) < 1e-4
+
+
+def test_feature_and_nonprivate_forward(dev, golden):
+    from eeg_multimodal_b200 import ConcatModel
+
+    p = ho.make_params(D, seed=3)
+    model = ConcatModel(private=False).to(dev)
+    load_params(model, p)
+    blocks = [torch.from_numpy(golden[k]) for k in ("eeg", "act", "cm")]
+    x = tuple(b.to(dev) for b in blocks)
+    assert torch.equal(model.feature(x).cpu(), ho.minmax_normalise(torch.cat(blocks, 1)))
+    assert rel_err(model(x), ho.head_forward_nonprivate(blocks, p)) < 1e-5
+
+
+def test_philox_forward_is_fresh_each_call_and_trainable(dev, golden):
+    from eeg_multimodal_b200 import ConcatModel, cal_loss
+
+    model = ConcatModel().to(dev)
+    model.eps = torch.tensor(1.0)
+    x = tuple(torch.from_numpy(golden[k]).to(dev).requires_grad_(True) for k in ("eeg", "act", "cm"))
+    a, b = model(x, hard=True), model(x, hard=True)
+    assert not torch.equal(a, b)                                       # fresh noise every forward (past_acc.py:131)
+    loss, _, _, _ = cal_loss(a, torch.from_numpy(golden["label"]).to(dev))
+    loss.backward()
+    assert all(t.grad is not None and torch.isfinite(t.grad).all() for t in x)   # grads reach the encoders
+    assert torch.isfinite(model.DP.grad).all() and float(model.DP.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("n_models", [1, 3])
+def test_engine_fp32_two_pass_step_matches_oracle(dev, golden, n_models):
+    """past_acc.py:198-212 for an ensemble: injected noise, 2 steps, Adam state carried over."""
+    from eeg_multimodal_b200 import HeadEngine
+
+    eps = [0.1, 1.0, 8.0][:n_models]
+    lr = 1e-3
+    eng = HeadEngine(n_models=n_models, eps=eps, lr=lr, precision="fp32")
+    blocks = [torch.from_numpy(golden[k]) for k in ("eeg", "act", "cm")]
+    label = torch.from_numpy(golden["label"])
+    trainers = []
+    for i in range(n_models):
+        p = ho.make_params(D, seed=20 + i, dp=golden_dp(golden, "wvalues"))
+        eng.load_state_dict(i, {"fc_layers.0.weight": p.W1, "fc_layers.0.bias": p.b1, "fc_layers.2.weight": p.W2,
+                                "fc_layers.2.bias": p.b2, "classifier.weight": p.Wc, "classifier.bias": p.bc, "DP": p.DP}, strict=True)
+        trainers.append(ho.TwoPassTrainer(p, eps[i], lr=lr))
+    dblocks = [b.to(dev) for b in blocks]
+    for step in range(2):
+        noises = [[ho.replay_reference_draws(1000 * step + 10 * i + k, 8, D) for k in range(2)] for i in range(n_models)]
+        ref_stats = []
+        for i, tr in enumerate(trainers):
+            (n1, g1), (n2, g2) = noises[i]
+            ref_stats.append(tr.step(blocks, label, n1, g1, n2, g2))
+        # engine: inject pass-1 noise, run pass 1; inject pass-2 noise, run pass 2 (same order as train_step)
+        lab = eng._labels(label.to(dev))
+        eng.inject_noise(torch.stack([noises[i][0][0] for i in range(n_models)]).to(dev),
+                         torch.stack([noises[i][0][1] for i in range(n_models)]).to(dev))
+        eng._pass(dblocks, lab, hard=False, mode="dp")
+        eng.t_dp += 1
+        from eeg_multimodal_b200 import ops
+
+        ops.adam_step(eng.DP, eng.dDP, eng.DP_m, eng.DP_v, eng.t_dp, lr)
+        eng.inject_noise(torch.stack([noises[i][1][0] for i in range(n_models)]).to(dev),
+                         torch.stack([noises[i][1][1] for i in range(n_models)]).to(dev))
+        res = eng._pass(dblocks, lab, hard=True, mode="model")
+        eng.t_model += 1
+        ops.adam_step(eng.flat, eng.grad, eng.m, eng.v, eng.t_model, lr)
+        st = res["stats"].view(n_models, 4).cpu()
+        for i, tr in enumerate(trainers):
+            assert abs(float(st[i, 0]) - ref_stats[i][0]) < 1e-5 * max(1.0, ref_stats[i][0])
+            assert abs(float(st[i, 2]) - ref_stats[i][1]) < 1e-6
+            assert torch.equal(res["pred"][i].cpu(), ref_stats[i][2])
+            sd = eng.state_dict(i)
+            for k, ref in (("fc_layers.0.weight", tr.p.W1), ("fc_layers.2.weight", tr.p.W2), ("classifier.weight", tr.p.Wc),
+                           ("fc_layers.0.bias", tr.p.b1), ("fc_layers.2.bias", tr.p.b2), ("classifier.bias", tr.p.bc), ("DP", tr.p.DP)):
+                diff = (sd[k].cpu() - ref.detach()).abs()
+                # Adam moves every weight by ~lr; 2% of that is the bar, and almost all entries are far tighter
+                assert float(diff.max()) < 0.02 * lr * (step + 1), (k, float(diff.max()))
+                assert float((diff > 1e-3 * lr).float().mean()) < 1e-3, k
+
+
+def test_engine_train_step_philox_learns(dev):
+    """End-to-end sanity on separable synthetic data: loss goes down, accuracy goes up, DP moves."""
+    from eeg_multimodal_b200 import HeadEngine
+
+    g = torch.Generator().manual_seed(0)
+    B, dims = 64, (768, 768, 768)
+    labels = (torch.rand(B, generator=g) < 0.66).long()
+    blocks = [torch.rand(B, d, generator=g) for d in dims]
+    blocks[0][:, :64] += labels[:, None].float() * 2.0
+    eng = HeadEngine(n_models=2, eps=[1.0, 8.0], lr=1e-4, precision="fp32", feature_dims=dims)
+    db, dl = [b.to(dev) for b in blocks], labels.to(dev)
+    first = eng.train_step(db, dl)
+    for _ in range(60):
+        last = eng.train_step(db, dl)
+    assert bool((last["loss"] < first["loss"]).all()) and bool((last["acc"] >= 0.9).all())
+    assert float(eng.DP.abs().max()) > 0
+    ev = eng.eval_step(db, dl)
+    assert ev["pred"].shape == (2, B) and bool((ev["acc"] >= 0.9).all())
+
+
+@pytest.mark.parametrize("B", [256, 1000])
+def test_engine_bf16_tensor_core_path_matches_oracle(dev, B):
+    """bf16 GEMM inputs, fp32 accumulate: logits/loss/gradients within 2e-2 of the fp32 oracle."""
+    from eeg_multimodal_b200 import HeadEngine
+
+    dims, Dd, H = (2048, 512), 2560, 768
+    g = torch.Generator().manual_seed(B)
+    blocks = [torch.rand(B, d, generator=g) for d in dims]
+    label = (torch.rand(B, 1, generator=g) < 0.66).long()
+    eng = HeadEngine(n_models=1, feature_dims=dims, eps=1.0, lr=1e-3, precision="bf16")
+    p = ho.make_params(Dd, H, seed=5, dp=(torch.randn(Dd, generator=g) * 0.1).numpy())
+    eng.load_state_dict(0, {"fc_layers.0.weight": p.W1, "fc_layers.0.bias": p.b1, "fc_layers.2.weight": p.W2,
+                            "fc_layers.2.bias": p.b2, "classifier.weight": p.Wc, "classifier.bias": p.bc, "DP": p.DP}, strict=True)
+    lap, gum = ho.replay_reference_draws(4, B, Dd)
+    db, lab = [b.to(dev) for b in blocks], eng._labels(label.to(dev))
+    for mode, hard in (("dp", False), ("model", True)):
+        po = p.clone(requires_grad=True)
+        pred = ho.head_forward(blocks, po, 1.0, lap, gum, hard)
+        loss, acc, pid, _ = ho.cal_loss(pred, label)
+        loss.backward()
+        eng.inject_noise(lap[None].to(dev), None)
+        res = eng._pass(db, lab, hard=hard, mode=mode)
+        torch.cuda.synchronize()
+        assert rel_err(res["logits"][0], pred) < 2e-2
+        assert abs(float(res["stats"][0, 0]) - float(loss.detach())) < 2e-2
+        agree = float((res["pred"][0].cpu() == pid).float().mean())
+        assert agree > 0.97                                               # argmax may flip only on near-ties in bf16
+        if mode == "dp":
+            assert rel_err(eng.dDP[0], po.DP.grad.view(-1)) < 2e-2
+        else:
+            for name, ref in (("W1", po.W1.grad), ("W2", po.W2.grad), ("b1", po.b1.grad), ("b2", po.b2.grad),
+                              ("Wc", po.Wc.grad), ("bc", po.bc.grad)):
+                assert rel_err(eng.view(name, eng.grad)[0], ref) < 2e-2, name
