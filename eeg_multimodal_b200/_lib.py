@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpgfuse.so")
 DT_F32, DT_BF16 = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32 = range(7)
+EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32, EPI_BIAS_TANH_F32 = range(8)
 
 P, I, LL, F, U32, U64, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint, C.c_ulonglong, C.c_size_t
 
@@ -23,10 +23,10 @@ SIGNATURES = {
     "pgf_version": (I, []),
     "pgf_last_error": (C.c_char_p, []),
     "pgf_num_sms": (I, []),
-    "pgf_dp_coeffs": (I, [P, F, I, I, P, P, P, P]),
-    "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, P]),
-    "pgf_perturb_gate_bwd_dp_workspace": (SZ, [I, I]),
-    "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, I, I, I, P, U64, U32, U64, P, P, SZ, P, I, P]),
+    "pgf_dp_coeffs": (I, [P, P, I, I, I, P, P, P, P]),
+    "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, I, LL, LL, LL, LL, LL, U64, P]),
+    "pgf_perturb_gate_bwd_dp_workspace": (SZ, [I, I, I]),
+    "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, LL, I, I, I, I, P, U64, U64, U32, U64, P, LL, P, SZ, P, LL, I, P]),
     "pgf_minmax_norm_bwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, I, LL, I, P, LL, P, LL, P, LL, P]),
     "pgf_linear_fwd": (I, [P, LL, LL, P, LL, P, LL, P, LL, LL, I, I, I, I, I, P]),
     "pgf_linear_bwd_dx_workspace": (SZ, [I, I, I, I]),

@@ -42,18 +42,22 @@ int pgf_version(void) { return 100; }
 const char* pgf_last_error(void) { return g_err; }
 int pgf_num_sms(void) { return num_sms(); }
 
-int pgf_dp_coeffs(const float* DP, float exp_eps, int fixed_formula, int D, float* w, float* eps_hat, float* deps_dDP,
-                  void* stream) {
-  PGF_CHECK_ARG(DP && D > 0, "pgf_dp_coeffs: DP is NULL or D <= 0");
-  return dp_coeffs(DP, exp_eps, fixed_formula, D, w, eps_hat, deps_dDP, static_cast<cudaStream_t>(stream));
+int pgf_dp_coeffs(const float* DP, const float* exp_eps, int fixed_formula, int D, int n_models, float* w, float* eps_hat,
+                  float* deps_dDP, void* stream) {
+  PGF_CHECK_ARG(DP && exp_eps && D > 0 && n_models > 0, "pgf_dp_coeffs: DP / exp_eps is NULL or D, n_models <= 0");
+  return dp_coeffs(DP, exp_eps, fixed_formula, D, n_models, w, eps_hat, deps_dDP, static_cast<cudaStream_t>(stream));
 }
 
 int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
                          int d2, long long ld2, const float* w, const float* eps_hat, int B, int noise_mode,
                          const float* lap, const float* gum, unsigned long long seed, unsigned int offset,
                          unsigned long long row0, float tau, int hard, int want_gate, void* out, int out_dtype,
-                         long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, void* stream) {
-  if (B == 0) return PGF_OK;  // empty batch: nothing to do
+                         long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, int n_models,
+                         long long sx0, long long sx1, long long sx2, long long s_coef, long long s_out,
+                         unsigned long long seed_step, void* stream) {
+  if (B == 0 || n_models == 0) return PGF_OK;  // empty batch: nothing to do
+  PGF_CHECK_ARG(n_models > 0 && (sx0 % 4) == 0 && (sx1 % 4) == 0 && (sx2 % 4) == 0 && (s_coef % 4) == 0 && (s_out % 4) == 0,
+                "pgf_perturb_gate_fwd: n_models < 0 or model strides not multiples of 4");
   PGF_CHECK_ARG(B > 0, "pgf_perturb_gate_fwd: B < 0");
   PGF_CHECK_ARG(x0 && d0 > 0, "pgf_perturb_gate_fwd: first feature block is required");
   PGF_CHECK_ARG(d1 >= 0 && d2 >= 0 && (d1 == 0 || x1) && (d2 == 0 || x2), "pgf_perturb_gate_fwd: block pointer/size mismatch");
@@ -72,9 +76,11 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   PerturbFwdArgs a;
   a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
   a.ld[0] = ld0; a.ld[1] = ld1; a.ld[2] = ld2;
+  a.sx[0] = sx0; a.sx[1] = sx1; a.sx[2] = sx2;
   a.d[0] = d0; a.d[1] = d1; a.d[2] = d2;
   a.D = d0 + d1 + d2;
   a.B = B;
+  a.n_models = n_models; a.s_coef = s_coef; a.s_out = s_out; a.seed_step = seed_step;
   a.w = w; a.eps_hat = eps_hat; a.lap = lap; a.gum = gum;
   a.seed = seed; a.offset = offset; a.row0 = row0;
   a.tau = tau; a.inv_tau = 1.0f / tau; a.hard = hard;
@@ -82,25 +88,30 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   return perturb_gate_fwd(a, noise_mode, out_dtype, gate, static_cast<cudaStream_t>(stream));
 }
 
-size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D) {
-  if (B <= 0 || D <= 0) return 0;
-  return static_cast<size_t>(perturb_bwd_slabs(B, D)) * D * sizeof(float);
+size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D, int n_models) {
+  if (B <= 0 || D <= 0 || n_models <= 0) return 0;
+  return static_cast<size_t>(n_models) * perturb_bwd_slabs(B, D, n_models) * D * sizeof(float);
 }
 
-int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, int B, int D, int noise_mode, const float* lap,
-                            unsigned long long seed, unsigned int offset, unsigned long long row0, const float* deps_dDP,
-                            float* workspace, size_t workspace_bytes, float* dDP, int accumulate, void* stream) {
-  PGF_CHECK_ARG(D > 0 && (D % 4) == 0 && dDP && deps_dDP, "pgf_perturb_gate_bwd_dp: bad D / NULL outputs");
+int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, long long s_dF, int B, int D, int n_models,
+                            int noise_mode, const float* lap, unsigned long long seed, unsigned long long seed_step,
+                            unsigned int offset, unsigned long long row0, const float* deps_dDP, long long s_coef,
+                            float* workspace, size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate,
+                            void* stream) {
+  PGF_CHECK_ARG(D > 0 && (D % 4) == 0 && dDP && deps_dDP && n_models >= 0, "pgf_perturb_gate_bwd_dp: bad D / NULL outputs");
+  if (n_models == 0) return PGF_OK;
   if (B == 0) {
-    if (!accumulate) cudaMemsetAsync(dDP, 0, sizeof(float) * D, static_cast<cudaStream_t>(stream));
+    if (!accumulate)
+      for (int m = 0; m < n_models; ++m) cudaMemsetAsync(dDP + m * s_dDP, 0, sizeof(float) * D, static_cast<cudaStream_t>(stream));
     return PGF_OK;
   }
-  PGF_CHECK_ARG(B > 0 && dF && aligned16(dF) && (ld % 4) == 0, "pgf_perturb_gate_bwd_dp: dF must be 16-byte aligned");
+  PGF_CHECK_ARG(B > 0 && dF && aligned16(dF) && (ld % 4) == 0 && (s_dF % 4) == 0,
+                "pgf_perturb_gate_bwd_dp: dF must be 16-byte aligned");
   PGF_CHECK_ARG(noise_mode == PGF_NOISE_INJECTED || noise_mode == PGF_NOISE_PHILOX, "pgf_perturb_gate_bwd_dp: bad noise_mode");
   if (noise_mode == PGF_NOISE_INJECTED) PGF_CHECK_ARG(lap, "pgf_perturb_gate_bwd_dp: injected mode needs lap");
   PGF_CHECK_ARG(workspace, "pgf_perturb_gate_bwd_dp: workspace is NULL");
-  return perturb_gate_bwd_dp(dF, dF_dtype, ld, B, D, noise_mode, lap, seed, offset, row0, deps_dDP, workspace,
-                             workspace_bytes, dDP, accumulate, static_cast<cudaStream_t>(stream));
+  return perturb_gate_bwd_dp(dF, dF_dtype, ld, s_dF, B, D, n_models, noise_mode, lap, seed, seed_step, offset, row0, deps_dDP,
+                             s_coef, workspace, workspace_bytes, dDP, s_dDP, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int pgf_minmax_norm_bwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
@@ -180,8 +191,8 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
                   int M, int N, int K, int epi, const float* bias, const void* aux, long long ld_aux, int stream_k,
                   void* stream) {
   PGF_CHECK_ARG(A && B && C, "pgf_gemm_bf16: NULL operand");
-  PGF_CHECK_ARG(epi >= 0 && epi <= 6, "pgf_gemm_bf16: bad epilogue %d", epi);
-  if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32)
+  PGF_CHECK_ARG(epi >= 0 && epi <= 7, "pgf_gemm_bf16: bad epilogue %d", epi);
+  if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32 || epi == PGF_EPI_BIAS_TANH_F32)
     PGF_CHECK_ARG(bias && aligned16(bias), "pgf_gemm_bf16: epilogue needs a 16-byte aligned bias");
   if (epi == PGF_EPI_RELUMASK_BF16) PGF_CHECK_ARG(aux && aligned16(aux) && (ld_aux % 8) == 0, "pgf_gemm_bf16: epilogue needs aux");
   GemmArgs g;

@@ -200,7 +200,7 @@ static int launch_ce(const CeArgs& a, int h_dtype, int dz_dtype, bool bwd, int n
   const size_t smem = bwd ? static_cast<size_t>(8) * 2 * a.H * sizeof(float) : 0;
 #define PGF_CE_LAUNCH(HT, DT, BW)                                                                        \
   do {                                                                                                   \
-    if (smem > 48 * 1024)                                                                                \
+    if (smem > 32 * 1024)                                                                                \
       cudaFuncSetAttribute(cls_ce_kernel<NV, HT, DT, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                            static_cast<int>(smem));                                                      \
     cls_ce_kernel<NV, HT, DT, BW><<<grid, block, smem, s>>>(a);                                          \

@@ -33,6 +33,7 @@ namespace pgf {
 #define PGF_EPI_ATOMIC_F32 4        // C(fp32) += acc                    (stream-K partials)
 #define PGF_EPI_STORE_F32 5         // C(fp32) = acc
 #define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
+#define PGF_EPI_BIAS_TANH_F32 7     // C(fp32) = tanh(acc + bias[n])
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
@@ -280,7 +281,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32) {
+          if (g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32 ||
+              g.epi == PGF_EPI_BIAS_TANH_F32) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               if (n + i < g.N) {
@@ -291,7 +293,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (g.epi == PGF_EPI_BIAS_RELU_BF16) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-            } else if (g.epi == PGF_EPI_BIAS_TANH_BF16) {
+            } else if (g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_TANH_F32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
             }
@@ -316,7 +318,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
               if (n + i < g.N) red_add_v4(cp + i, f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else if (g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32) {
+          } else if (g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 || g.epi == PGF_EPI_BIAS_TANH_F32) {
             float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n;
 #pragma unroll
             for (int i = 0; i < 32; i += 4)

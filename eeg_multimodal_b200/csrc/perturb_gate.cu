@@ -48,68 +48,102 @@ __device__ __forceinline__ float gate_faithful(float f, float w, float g0, float
   return __fadd_rn(__fmul_rn(f, m0), __fmul_rn(f, m1));
 }
 
+constexpr int FWD_THREADS = 128;  // 4 warps share one row: <= 8 float4 per lane, ~64 registers, 32 warps/SM
+
 template <int NV, int NOISE, typename OutT, bool WANT_GATE>
-__global__ void __launch_bounds__(256) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
   extern __shared__ float4 smem4[];
-  float4* s_eps = smem4;                 // [D/4]
-  float4* s_w = smem4 + (a.D >> 2);      // [D/4] (only when the gate is evaluated)
+  __shared__ float s_part[2][FWD_THREADS / 32][3];  // [parity][warp]{min, max, nan-probe}
+  float4* s_eps = smem4;                 // [D/4]  eps_hat (Philox mode: pre-multiplied by -ln2)
+  float4* s_w = smem4 + (a.D >> 2);      // [D/4]  (only when the gate is evaluated)
+  const int model = blockIdx.y;
   const int nvec = a.D >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (NOISE != PGF_NOISE_NONE) {
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-      s_eps[i] = reinterpret_cast<const float4*>(a.eps_hat)[i];
-      if (WANT_GATE) s_w[i] = reinterpret_cast<const float4*>(a.w)[i];
+    const float4* ge = reinterpret_cast<const float4*>(a.eps_hat + model * a.s_coef);
+    const float4* gw = reinterpret_cast<const float4*>(a.w + model * a.s_coef);
+    for (int i = tid; i < nvec; i += FWD_THREADS) {
+      float4 e = ge[i];
+      if (NOISE == PGF_NOISE_PHILOX) {  // fold -ln(2) of  -ln(v) = -ln2 * lg2(v)  into the coefficient
+        e.x *= -0.69314718055994531f; e.y *= -0.69314718055994531f;
+        e.z *= -0.69314718055994531f; e.w *= -0.69314718055994531f;
+      }
+      s_eps[i] = e;
+      if (WANT_GATE) s_w[i] = gw[i];
     }
     __syncthreads();
   }
-  const int lane = threadIdx.x & 31;
-  const int warps_per_cta = blockDim.x >> 5;
   const int d01 = a.d[0] + a.d[1];
-  const unsigned int k0 = static_cast<unsigned int>(a.seed), k1 = static_cast<unsigned int>(a.seed >> 32);
+  const float* x0 = a.x[0] + model * a.sx[0];
+  const float* x1 = a.d[1] ? a.x[1] + model * a.sx[1] : nullptr;
+  const float* x2 = a.d[2] ? a.x[2] + model * a.sx[2] : nullptr;
+  const unsigned long long seed = a.seed + static_cast<unsigned long long>(model) * a.seed_step;
+  const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
+  const long long BD = static_cast<long long>(a.B) * a.D;
+  const float* lap = a.lap ? a.lap + model * BD : nullptr;
+  const float* gum = a.gum ? a.gum + model * 2 * BD : nullptr;
+  unsigned char* gate_idx = a.gate_idx ? a.gate_idx + model * BD : nullptr;
 
-  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); row < a.B;
-       row += static_cast<long long>(gridDim.x) * warps_per_cta) {
+  int it = 0;
+  for (long long row = blockIdx.x; row < a.B; row += gridDim.x, ++it) {
     float4 v[NV];
-    float mn = INFINITY, mx = -INFINITY;
-    bool has_nan = false;
+    float mn = INFINITY, mx = -INFINITY, probe = 0.f;
     // ---- fused concat load (models.py:69): all loads issued before first use
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int col = (lane + 32 * k) << 2;
+      const int col = (tid + FWD_THREADS * k) << 2;
       if (col < a.D) {
         const float* p;
         if (col < a.d[0])
-          p = a.x[0] + row * a.ld[0] + col;
+          p = x0 + row * a.ld[0] + col;
         else if (col < d01)
-          p = a.x[1] + row * a.ld[1] + (col - a.d[0]);
+          p = x1 + row * a.ld[1] + (col - a.d[0]);
         else
-          p = a.x[2] + row * a.ld[2] + (col - d01);
+          p = x2 + row * a.ld[2] + (col - d01);
         v[k] = ldg_stream(reinterpret_cast<const float4*>(p));
       }
     }
-    // ---- row min / max (models.py:70-71); torch.min/max propagate NaN
+    // ---- row min / max (models.py:70-71).  torch.min/max propagate NaN while fminf/fmaxf drop it, so
+    // a running sum is carried as a NaN probe (NaN in -> NaN out; an inf/-inf mix also gives the NaN
+    // row the reference produces).
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int col = (lane + 32 * k) << 2;
+      const int col = (tid + FWD_THREADS * k) << 2;
       if (col < a.D) {
         mn = fminf(fminf(mn, v[k].x), fminf(v[k].y, fminf(v[k].z, v[k].w)));
         mx = fmaxf(fmaxf(mx, v[k].x), fmaxf(v[k].y, fmaxf(v[k].z, v[k].w)));
-        has_nan |= (v[k].x != v[k].x) | (v[k].y != v[k].y) | (v[k].z != v[k].z) | (v[k].w != v[k].w);
+        probe += (v[k].x + v[k].y) + (v[k].z + v[k].w);
       }
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
-    if (__any_sync(0xffffffffu, has_nan)) mn = mx = __int_as_float(0x7fc00000);
+    probe = warp_sum(probe);
+    float(*part)[3] = s_part[it & 1];
+    if (lane == 0) {
+      part[warp][0] = mn;
+      part[warp][1] = mx;
+      part[warp][2] = probe;
+    }
+    __syncthreads();  // one barrier per row: the partial slots are double-buffered on the row parity
+#pragma unroll
+    for (int w = 0; w < FWD_THREADS / 32; ++w) {
+      mn = fminf(mn, part[w][0]);
+      mx = fmaxf(mx, part[w][1]);
+    }
+    probe = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
+    if (probe != probe) mn = mx = __int_as_float(0x7fc00000);
     const float range = __fsub_rn(mx, mn);
     const float inv_range = __frcp_rn(range);
-    if (lane == 0) {
-      if (a.row_min) a.row_min[row] = mn;
-      if (a.row_max) a.row_max[row] = mx;
+    if (tid == 0) {
+      if (a.row_min) a.row_min[model * a.B + row] = mn;
+      if (a.row_max) a.row_max[model * a.B + row] = mx;
     }
     const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+    char* outp = static_cast<char*>(a.out) + model * a.s_out * static_cast<long long>(sizeof(OutT));
 
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int j = lane + 32 * k;
+      const int j = tid + FWD_THREADS * k;
       const int col = j << 2;
       if (col < a.D) {
         float f[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
@@ -126,27 +160,26 @@ __global__ void __launch_bounds__(256) perturb_gate_fwd_kernel(const PerturbFwdA
         if (NOISE == PGF_NOISE_INJECTED) {
           const float4 e4 = s_eps[j];
           const float eh[4] = {e4.x, e4.y, e4.z, e4.w};
-          const float4 l4 = ldg_stream(reinterpret_cast<const float4*>(a.lap + row * a.D + col));
+          const float4 l4 = ldg_stream(reinterpret_cast<const float4*>(lap + row * a.D + col));
           const float lp[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] = __fadd_rn(f[e], __fmul_rn(lp[e], eh[e]));  // :76
           if (WANT_GATE) {                                                               // :77-79
             const float4 w4 = s_w[j];
             const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-            const float4 g0 = ldg_stream(reinterpret_cast<const float4*>(a.gum + row * a.D + col));
-            const float4 g1 =
-                ldg_stream(reinterpret_cast<const float4*>(a.gum + (static_cast<long long>(a.B) + row) * a.D + col));
+            const float4 g0 = ldg_stream(reinterpret_cast<const float4*>(gum + row * a.D + col));
+            const float4 g1 = ldg_stream(reinterpret_cast<const float4*>(gum + BD + row * a.D + col));
             const float ga[4] = {g0.x, g0.y, g0.z, g0.w}, gb[4] = {g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) f[e] = gate_faithful(f[e], ww[e], ga[e], gb[e], a.tau, a.hard, idx[e]);
           }
         } else if (NOISE == PGF_NOISE_PHILOX) {
           const float4 e4 = s_eps[j];
-          const float eh[4] = {e4.x, e4.y, e4.z, e4.w};
+          const float eh[4] = {e4.x, e4.y, e4.z, e4.w};  // = -ln2 * eps_hat
           const uint4 r = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) f[e] = fmaf(laplace_from_bits(rb[e]), eh[e], f[e]);
+          for (int e = 0; e < 4; ++e) f[e] += laplace_scaled_from_bits(rb[e], eh[e]);
           if (WANT_GATE) {
             // The two mask planes sum to one (hard: exactly, soft: within 1 ulp), so the gated
             // value IS the perturbed value; only the gate index is a real output.
@@ -163,10 +196,10 @@ __global__ void __launch_bounds__(256) perturb_gate_fwd_kernel(const PerturbFwdA
             }
           }
         }
-        store_out4<OutT>(a.out, row * a.ld_out + col, make_float4(f[0], f[1], f[2], f[3]));
-        if (WANT_GATE && a.gate_idx) {
+        store_out4<OutT>(outp, row * a.ld_out + col, make_float4(f[0], f[1], f[2], f[3]));
+        if (WANT_GATE && gate_idx) {
           const unsigned int packed = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-          *reinterpret_cast<unsigned int*>(a.gate_idx + row * a.D + col) = packed;
+          *reinterpret_cast<unsigned int*>(gate_idx + row * a.D + col) = packed;
         }
       }
     }
@@ -175,16 +208,16 @@ __global__ void __launch_bounds__(256) perturb_gate_fwd_kernel(const PerturbFwdA
 
 template <int NV, int NOISE, typename OutT>
 static int launch_fwd_gate(const PerturbFwdArgs& a, bool want_gate, cudaStream_t stream) {
-  const int threads = 256;
-  int grid = num_sms() * 2;
-  const int max_grid = (a.B + 7) / 8;
-  if (grid > max_grid) grid = max_grid;
-  if (grid < 1) grid = 1;
   const size_t smem = (NOISE == PGF_NOISE_NONE) ? 0 : static_cast<size_t>(a.D) * sizeof(float) * (want_gate ? 2 : 1);
+  // persistent CTAs: ~8 per SM in total (register-limited residency), each looping over rows
+  int gx = (num_sms() * 8 + a.n_models - 1) / a.n_models;
+  if (gx > a.B) gx = a.B;
+  if (gx < 1) gx = 1;
+  const dim3 grid(gx, a.n_models);
   if (want_gate)
-    perturb_gate_fwd_kernel<NV, NOISE, OutT, true><<<grid, threads, smem, stream>>>(a);
+    perturb_gate_fwd_kernel<NV, NOISE, OutT, true><<<grid, FWD_THREADS, smem, stream>>>(a);
   else
-    perturb_gate_fwd_kernel<NV, NOISE, OutT, false><<<grid, threads, smem, stream>>>(a);
+    perturb_gate_fwd_kernel<NV, NOISE, OutT, false><<<grid, FWD_THREADS, smem, stream>>>(a);
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_fwd");
   return PGF_OK;
 }
@@ -203,10 +236,10 @@ static int launch_fwd_nv(const PerturbFwdArgs& a, int noise, int out_dtype, bool
 }
 
 int perturb_gate_fwd(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
-  const int nv = (a.D / 4 + 31) / 32;
+  const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
+  if (nv <= 2) return launch_fwd_nv<2>(a, noise, out_dtype, want_gate, s);
+  if (nv <= 5) return launch_fwd_nv<5>(a, noise, out_dtype, want_gate, s);
   if (nv <= 8) return launch_fwd_nv<8>(a, noise, out_dtype, want_gate, s);
-  if (nv <= 20) return launch_fwd_nv<20>(a, noise, out_dtype, want_gate, s);
-  if (nv <= 32) return launch_fwd_nv<32>(a, noise, out_dtype, want_gate, s);
   set_error("pgf_perturb_gate_fwd: fused width D=%d exceeds the register-resident limit 4096", a.D);
   return PGF_ERR_UNSUPPORTED;
 }
@@ -221,9 +254,12 @@ int perturb_gate_fwd(const PerturbFwdArgs& a, int noise, int out_dtype, bool wan
 struct PerturbBwdArgs {
   const void* dF;
   long long ld;
+  long long s_dF;
   int B, D;
   const float* lap;
   unsigned long long seed;
+  unsigned long long seed_step;
+  int nslab;
   unsigned int offset;
   unsigned long long row0;
   int rows_per_slab;
@@ -248,21 +284,24 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column index
   const int col = j << 2;
   if (col >= a.D) return;
-  const int slab = blockIdx.y;
+  const int slab = blockIdx.y, model = blockIdx.z;
   const int r0 = slab * a.rows_per_slab;
   const int r1 = min(a.B, r0 + a.rows_per_slab);
-  const unsigned int k0 = static_cast<unsigned int>(a.seed), k1 = static_cast<unsigned int>(a.seed >> 32);
+  const unsigned long long seed = a.seed + static_cast<unsigned long long>(model) * a.seed_step;
+  const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
+  const void* dFm = static_cast<const char*>(a.dF) + model * a.s_dF * static_cast<long long>(sizeof(InT));
+  const float* lapm = a.lap ? lapm + static_cast<long long>(model) * a.B * a.D : nullptr;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  constexpr int U = 4;
+  constexpr int U = 8;
   int r = r0;
   for (; r + U <= r1; r += U) {
     float4 g[U], l[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) g[u] = load_in4<InT>(a.dF, static_cast<long long>(r + u) * a.ld + col);
+    for (int u = 0; u < U; ++u) g[u] = load_in4<InT>(dFm, static_cast<long long>(r + u) * a.ld + col);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (NOISE == PGF_NOISE_INJECTED) {
-        l[u] = ldg_stream(reinterpret_cast<const float4*>(a.lap + static_cast<long long>(r + u) * a.D + col));
+        l[u] = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r + u) * a.D + col));
       } else {
         const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
                                       PGF_STREAM_LAPLACE, a.offset, k0, k1);
@@ -279,10 +318,10 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
     }
   }
   for (; r < r1; ++r) {
-    const float4 g = load_in4<InT>(a.dF, static_cast<long long>(r) * a.ld + col);
+    const float4 g = load_in4<InT>(dFm, static_cast<long long>(r) * a.ld + col);
     float4 l;
     if (NOISE == PGF_NOISE_INJECTED) {
-      l = ldg_stream(reinterpret_cast<const float4*>(a.lap + static_cast<long long>(r) * a.D + col));
+      l = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r) * a.D + col));
     } else {
       const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
                                     PGF_STREAM_LAPLACE, a.offset, k0, k1);
@@ -293,22 +332,25 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
     acc.z = fmaf(g.z, l.z, acc.z);
     acc.w = fmaf(g.w, l.w, acc.w);
   }
-  *reinterpret_cast<float4*>(a.partial + static_cast<long long>(slab) * a.D + col) = acc;
+  *reinterpret_cast<float4*>(a.partial + (static_cast<long long>(model) * a.nslab + slab) * a.D + col) = acc;
 }
 
 __global__ void perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
-                                               const float* __restrict__ coef, float* __restrict__ dDP,
-                                               float accumulate) {
+                                               const float* __restrict__ coef, long long s_coef,
+                                               float* __restrict__ dDP, long long s_dDP, float accumulate) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int model = blockIdx.y;
   if (d >= D) return;
+  const float* P = partial + static_cast<long long>(model) * nslab * D;
   float s = 0.f;
-  for (int i = 0; i < nslab; ++i) s += partial[static_cast<long long>(i) * D + d];
-  const float v = s * coef[d];
-  dDP[d] = accumulate != 0.f ? dDP[d] + v : v;
+  for (int i = 0; i < nslab; ++i) s += P[static_cast<long long>(i) * D + d];
+  const float v = s * coef[model * s_coef + d];
+  float* o = dDP + model * s_dDP + d;
+  *o = accumulate != 0.f ? *o + v : v;
 }
 
-int perturb_bwd_slabs(int B, int D) {
-  const int col_ctas = (D / 4 + 127) / 128;
+int perturb_bwd_slabs(int B, int D, int n_models) {
+  const int col_ctas = (D / 4 + 127) / 128 * (n_models > 0 ? n_models : 1);
   int slabs = (num_sms() * 4 + col_ctas - 1) / col_ctas;
   const int max_slabs = (B + 31) / 32;
   if (slabs > max_slabs) slabs = max_slabs;
@@ -316,27 +358,31 @@ int perturb_bwd_slabs(int B, int D) {
   return slabs;
 }
 
-int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, int B, int D, int noise, const float* lap,
-                        unsigned long long seed, unsigned int offset, unsigned long long row0, const float* coef,
-                        float* workspace, size_t workspace_bytes, float* dDP, int accumulate, cudaStream_t s) {
-  const int slabs = perturb_bwd_slabs(B, D);
-  if (workspace_bytes < static_cast<size_t>(slabs) * D * sizeof(float)) {
-    set_error("pgf_perturb_gate_bwd_dp: workspace too small (%zu < %zu bytes)", workspace_bytes,
-              static_cast<size_t>(slabs) * D * sizeof(float));
+int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF, int B, int D, int n_models, int noise,
+                        const float* lap, unsigned long long seed, unsigned long long seed_step, unsigned int offset,
+                        unsigned long long row0, const float* coef, long long s_coef, float* workspace,
+                        size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate, cudaStream_t s) {
+  const int slabs = perturb_bwd_slabs(B, D, n_models);
+  const size_t need = static_cast<size_t>(n_models) * slabs * D * sizeof(float);
+  if (workspace_bytes < need) {
+    set_error("pgf_perturb_gate_bwd_dp: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return PGF_ERR_WORKSPACE;
   }
   PerturbBwdArgs a;
   a.dF = dF;
   a.ld = ld;
+  a.s_dF = s_dF;
   a.B = B;
   a.D = D;
   a.lap = lap;
   a.seed = seed;
+  a.seed_step = seed_step;
+  a.nslab = slabs;
   a.offset = offset;
   a.row0 = row0;
   a.rows_per_slab = (B + slabs - 1) / slabs;
   a.partial = workspace;
-  const dim3 grid((D / 4 + 127) / 128, slabs);
+  const dim3 grid((D / 4 + 127) / 128, slabs, n_models);
   if (noise == PGF_NOISE_INJECTED) {
     if (dtype == PGF_DT_F32)
       perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float><<<grid, 128, 0, s>>>(a);
@@ -349,8 +395,8 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, int B, int D, i
       perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16><<<grid, 128, 0, s>>>(a);
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
-  perturb_bwd_dp_finalize_kernel<<<(D + 255) / 256, 256, 0, s>>>(workspace, slabs, D, coef, dDP,
-                                                                accumulate ? 1.f : 0.f);
+  const dim3 fgrid((D + 255) / 256, n_models);
+  perturb_bwd_dp_finalize_kernel<<<fgrid, 256, 0, s>>>(workspace, slabs, D, coef, s_coef, dDP, s_dDP, accumulate ? 1.f : 0.f);
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp(finalize)");
   return PGF_OK;
 }
@@ -361,25 +407,30 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, int B, int D, i
 //   deps_dDP = d eps_hat / d DP = d eps_hat/dw * w(1-w)
 //     fixed:   -(E-1) w / (L^2 (E-w)),    unfixed:  (E-1) w / (E-w),   L = log((E-w)/(1-w))
 // ------------------------------------------------------------------------------------------
-__global__ void dp_coeffs_kernel(const float* __restrict__ DP, float exp_eps, int fixed, int D, float* __restrict__ w_out,
-                                 float* __restrict__ eps_hat, float* __restrict__ deps) {
+__global__ void dp_coeffs_kernel(const float* __restrict__ DP, const float* __restrict__ exp_eps_arr, int fixed, int D,
+                                 float* __restrict__ w_out, float* __restrict__ eps_hat, float* __restrict__ deps) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int model = blockIdx.y;
   if (d >= D) return;
-  const float x = DP[d];
+  const long long i = static_cast<long long>(model) * D + d;
+  const float exp_eps = exp_eps_arr[model];
+  const float x = DP[i];
   const float w = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
   const float num = __fsub_rn(exp_eps, w);
   const float ratio = __fdiv_rn(num, __fsub_rn(1.0f, w));
   const float L = logf(ratio);
-  if (w_out) w_out[d] = w;
-  if (eps_hat) eps_hat[d] = fixed ? __fdiv_rn(1.0f, L) : L;
+  if (w_out) w_out[i] = w;
+  if (eps_hat) eps_hat[i] = fixed ? __fdiv_rn(1.0f, L) : L;
   if (deps) {
     const float t = (exp_eps - 1.0f) * w / num;
-    deps[d] = fixed ? -t / (L * L) : t;
+    deps[i] = fixed ? -t / (L * L) : t;
   }
 }
 
-int dp_coeffs(const float* DP, float exp_eps, int fixed, int D, float* w, float* eps_hat, float* deps, cudaStream_t s) {
-  dp_coeffs_kernel<<<(D + 255) / 256, 256, 0, s>>>(DP, exp_eps, fixed, D, w, eps_hat, deps);
+int dp_coeffs(const float* DP, const float* exp_eps, int fixed, int D, int n_models, float* w, float* eps_hat, float* deps,
+              cudaStream_t s) {
+  const dim3 grid((D + 255) / 256, n_models);
+  dp_coeffs_kernel<<<grid, 256, 0, s>>>(DP, exp_eps, fixed, D, w, eps_hat, deps);
   PGF_CUDA_LAUNCH_CHECK("pgf_dp_coeffs");
   return PGF_OK;
 }

@@ -30,17 +30,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// Laplace(0,1): sign bit + 23-bit magnitude uniform, v=(m+0.5)*2^-23 exact in fp32.
+// Laplace(0,1): bit 31 = sign, bits 0..22 = magnitude uniform, v=(m+0.5)*2^-23 exact in fp32,
+// x = -+ln(v).  `laplace_scaled_from_bits(r, c)` returns x * eps_hat given c = -ln2 * eps_hat:
+// lg2(v) * c with the sign bit XOR-ed in (5 instructions + 1 MUFU).
+__device__ __forceinline__ float laplace_scaled_from_bits(uint32_t r, float c) {
+  const float v = fmaf(static_cast<float>(r & 0x7FFFFFu), 1.1920928955078125e-07f, 5.9604644775390625e-08f);
+  const float t = __log2f(v) * c;
+  return __uint_as_float(__float_as_uint(t) ^ (r & 0x80000000u));
+}
 __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
-  const float v = (static_cast<float>((r >> 8) & 0x7FFFFFu) + 0.5f) * 1.1920928955078125e-07f;
-  const float mag = -__logf(v);
-  return (r >> 31) ? -mag : mag;
+  return laplace_scaled_from_bits(r, -0.69314718055994531f);
 }
 
 // Gumbel(0,1) = -log(Exp(1)), Exp(1) = -log(v), v=((r>>9)+0.5)*2^-23.
 __device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
   const float v = (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
-  return -__logf(-__logf(v));
+  return -__logf(-logf(v));  // accurate inner log: E = -ln(v) can be tiny
 }
 
 }  // namespace pgf

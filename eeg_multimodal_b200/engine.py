@@ -48,7 +48,13 @@ class HeadEngine:
         assert len(eps_list) == self.M
         self.eps = eps_list
         self.exp_eps = [exp_eps_of(e) for e in eps_list]
-        self.seeds = list(seeds) if seeds is not None else [REFERENCE_SEED + i for i in range(self.M)]
+        self.seeds = [int(x) for x in seeds] if seeds is not None else [REFERENCE_SEED + i for i in range(self.M)]
+        assert len(self.seeds) == self.M
+        steps = {self.seeds[i + 1] - self.seeds[i] for i in range(self.M - 1)}
+        # seeds in arithmetic progression -> the whole ensemble's noise is one grouped launch
+        self.seed_step = (steps.pop() if steps else 0) if len(steps) <= 1 else None
+        if self.seed_step is not None and self.seed_step < 0:
+            self.seed_step = None
         D, H, C = self.D, self.H, self.C
         sizes = [("W1", (D, D)), ("b1", (D,)), ("W2", (H, D)), ("b2", (H,)), ("Wc", (C, H)), ("bc", (C,))]
         self.layout, off = {}, 0
@@ -72,6 +78,7 @@ class HeadEngine:
         self.noise_offset = 0
         self._bufs = {}
         self._injected = None
+        self.exp_eps_dev = torch.tensor(self.exp_eps, dtype=torch.float32, device=dev)
         self._init_params(init_seed, dp_init)
 
     # ---- parameters ----------------------------------------------------------------------------
@@ -134,35 +141,46 @@ class HeadEngine:
         """Per-model injected noise for the NEXT pass: lap [M,B,D], gum [M,2,B,D] (parity tests)."""
         self._injected = (lap.contiguous(), None if gum is None else gum.contiguous())
 
-    def _perturb(self, blocks, hard, out, row0, want_coeffs=True):
-        """kernel (a) for every model; returns the per-model deps_dDP rows and the noise spec."""
+    def _perturb(self, blocks, hard, out, row0):
+        """kernel (a) for every model; returns the per-model coefficient rows and the noise spec."""
         M, D = self.M, self.D
-        coef = self._buf("coef", (M, 3, D), torch.float32)
+        coef = self._buf("coef", (3, M, D), torch.float32)
+        ops.dp_coeffs(self.DP, self.exp_eps_dev, self.fixed, out=coef)
         inj = self._injected
         self._injected = None
         offset = self.noise_offset
         self.noise_offset += 1
-        for i in range(M):
-            L.call("pgf_dp_coeffs", self.DP[i].data_ptr(), self.exp_eps[i], int(self.fixed), D, coef[i, 0].data_ptr(),
-                   coef[i, 1].data_ptr(), coef[i, 2].data_ptr(), ops._stream())
-            bl = [b[i] if b.dim() == 3 else b for b in blocks]
-            if inj is not None:
-                ops.perturb_gate_fwd(bl, coef[i, 0], coef[i, 1], noise_mode=L.NOISE_INJECTED, lap=inj[0][i],
-                                     gum=None if inj[1] is None else inj[1][i], tau=self.tau, hard=hard,
-                                     want_gate=inj[1] is not None, out=out[i])
-            else:
-                ops.perturb_gate_fwd(bl, coef[i, 0], coef[i, 1], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i],
-                                     offset=offset, row0=row0, tau=self.tau, hard=hard, want_gate=False, out=out[i])
+        if inj is not None:
+            ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_INJECTED, lap=inj[0], gum=inj[1], tau=self.tau,
+                                 hard=hard, want_gate=inj[1] is not None, out=out, n_models=M)
+        elif self.seed_step is not None:   # one grouped launch for the whole ensemble
+            ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, seed=self.seeds[0],
+                                 seed_step=self.seed_step, offset=offset, row0=row0, tau=self.tau, hard=hard, out=out, n_models=M)
+        else:
+            for i in range(M):
+                bl = [b[i] if b.dim() == 3 else b for b in blocks]
+                ops.perturb_gate_fwd(bl, coef[0, i], coef[1, i], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
+                                     row0=row0, tau=self.tau, hard=hard, out=out[i])
         return coef, (inj, offset)
+
+    def _dDP_one(self, i, dXi, coef, noise_spec, row0):
+        inj, offset = noise_spec
+        if inj is not None:
+            ops.perturb_gate_bwd_dp(dXi, coef[2, i], noise_mode=L.NOISE_INJECTED, lap=inj[0][i], out=self.dDP[i])
+        else:
+            ops.perturb_gate_bwd_dp(dXi, coef[2, i], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
+                                    row0=row0, out=self.dDP[i])
 
     def _dDP(self, dX, coef, noise_spec, row0):
         inj, offset = noise_spec
-        for i in range(self.M):
-            if inj is not None:
-                ops.perturb_gate_bwd_dp(dX[i], coef[i, 2], noise_mode=L.NOISE_INJECTED, lap=inj[0][i], out=self.dDP[i])
-            else:
-                ops.perturb_gate_bwd_dp(dX[i], coef[i, 2], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
-                                        row0=row0, out=self.dDP[i])
+        if inj is not None:
+            ops.perturb_gate_bwd_dp(dX, coef[2], noise_mode=L.NOISE_INJECTED, lap=inj[0], out=self.dDP)
+        elif self.seed_step is not None:
+            ops.perturb_gate_bwd_dp(dX, coef[2], noise_mode=L.NOISE_PHILOX, seed=self.seeds[0], seed_step=self.seed_step,
+                                    offset=offset, row0=row0, out=self.dDP)
+        else:
+            for i in range(self.M):
+                self._dDP_one(i, dX[i], coef, noise_spec, row0)
 
     def _labels(self, labels):
         labels = labels.reshape(labels.shape[0], -1)[:, 0] if labels.dim() == 2 and labels.shape[-1] == 1 else labels
@@ -201,13 +219,13 @@ class HeadEngine:
         X = self._buf("Xh", (M, B, D), bf)
         coef, nspec = self._perturb(blocks, hard, X, row0)
         H1 = self._buf("H1h", (M, B, D), bf)
-        H2 = self._buf("H2h", (M, B, H), bf)
+        H2 = self._buf("H2f", (M, B, H), torch.float32)  # tanh output kept in fp32: exact logits / loss
         W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
         for i in range(M):
             ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i])
-            ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_BF16, bias=b2[i])
+            ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2[i])
         res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
-                         dz=self._buf("dZ2h", (M, B, H), bf) if backward else None,
+                         dz=self._buf("dZ2h", (M, B, H), bf) if backward else None, dz_dtype=bf,
                          dWc=self.view("Wc", self.grad) if mode == "model" else None,
                          dbc=self.view("bc", self.grad) if mode == "model" else None)
         if mode == "eval":
@@ -218,10 +236,11 @@ class HeadEngine:
             # dZ1 = (dZ2 . W2) * relu'(H1):   B operand = W2 stored [K=H, N=D]  -> MN-major
             ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1[i])
         if mode == "dp":
-            dX = self._buf("dXh", (M, B, D), bf)
+            dX = self._buf("dXf", (B, D), torch.float32)   # fp32 out: feeds the dDP column reduction only
             for i in range(M):
-                ops.gemm_bf16(dZ1[i], W1h[i], dX[i], M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_BF16)
-            self._dDP(dX, coef, nspec, row0)
+                ops.gemm_bf16(dZ1[i], W1h[i], dX, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32)
+                self._dDP_one(i, dX, coef, nspec, row0)
+            return res
         else:
             gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
             gb1, gb2 = self.view("b1", self.grad), self.view("b2", self.grad)

@@ -43,7 +43,7 @@ class _PerturbGateFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, DP, exp_eps, cfg, *blocks):
-        w, eps_hat, deps = ops.dp_coeffs(DP.detach().reshape(-1), exp_eps, cfg.fixed)
+        w, eps_hat, deps = ops.dp_coeffs(DP.detach().reshape(-1).contiguous(), exp_eps, cfg.fixed)
         out, gate_idx, _, _ = ops.perturb_gate_fwd(
             [b.detach() for b in blocks], w, eps_hat, noise_mode=cfg.mode, lap=cfg.lap, gum=cfg.gum, seed=cfg.seed,
             offset=cfg.offset, row0=cfg.row0, tau=cfg.tau, hard=cfg.hard, want_gate=cfg.want_gate,

@@ -54,59 +54,87 @@ def workspace(tag: str) -> Workspace:
 
 
 # --------------------------------------------------------------------------------------------
-def dp_coeffs(DP: torch.Tensor, exp_eps: float, fixed: bool = True):
-    """(w, eps_hat, deps_dDP), each [D].  models.py:73,75."""
+def _exp_eps_tensor(exp_eps, n_models, device):
+    if isinstance(exp_eps, torch.Tensor):
+        t = exp_eps.to(device=device, dtype=torch.float32).reshape(-1)
+    else:
+        vals = list(exp_eps) if isinstance(exp_eps, (list, tuple)) else [exp_eps] * n_models
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float32, device=device)
+    assert t.numel() == n_models
+    return t.contiguous()
+
+
+def dp_coeffs(DP: torch.Tensor, exp_eps, fixed: bool = True, out=None):
+    """(w, eps_hat, deps_dDP), each shaped like DP ([D] or [n_models, D]).  models.py:73,75.
+    `exp_eps`: float (one model), list, or device tensor [n_models] of e^eps values."""
     _chk(DP, torch.float32, "DP")
-    D = DP.numel()
-    out = torch.empty(3, D, dtype=torch.float32, device=DP.device)
-    L.call("pgf_dp_coeffs", DP.data_ptr(), float(exp_eps), int(fixed), D, out[0].data_ptr(), out[1].data_ptr(),
+    assert DP.is_contiguous()
+    D = DP.shape[-1]
+    n_models = DP.numel() // D
+    ee = _exp_eps_tensor(exp_eps, n_models, DP.device)
+    if out is None:
+        out = torch.empty(3, *DP.shape, dtype=torch.float32, device=DP.device)
+    L.call("pgf_dp_coeffs", DP.data_ptr(), ee.data_ptr(), int(fixed), D, n_models, out[0].data_ptr(), out[1].data_ptr(),
            out[2].data_ptr(), _stream())
     return out[0], out[1], out[2]
 
 
 def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed=0, offset=0, row0=0, tau=1.0,
                      hard=True, want_gate=False, out_dtype=torch.float32, out=None, want_gate_idx=False,
-                     want_minmax=False):
-    """models.py:69-79 in one kernel.  Returns (out[B,D], gate_idx|None, row_min|None, row_max|None)."""
+                     want_minmax=False, n_models=1, seed_step=0):
+    """models.py:69-79 in one kernel.  Returns (out, gate_idx|None, row_min|None, row_max|None).
+    Single model: blocks [B,Di], out [B,D].  Grouped (n_models > 1): blocks [B,Di] (shared batch) or
+    [M,B,Di]; w/eps_hat [M,D]; out [M,B,D]; lap [M,B,D]; gum [M,2,B,D]; model m uses seed + m*seed_step."""
     blocks = [_chk(b, torch.float32, "feature block") for b in blocks]
     if not 1 <= len(blocks) <= 3:
         raise ValueError("1 to 3 feature blocks expected")
-    B = blocks[0].shape[0]
-    dims = [b.shape[1] for b in blocks]
+    B = blocks[0].shape[-2]
+    dims = [b.shape[-1] for b in blocks]
     D = sum(dims)
     dev = blocks[0].device
+    M = int(n_models)
+    lead = (M,) if M > 1 or (out is not None and out.dim() == 3) else ()
     if out is None:
-        out = torch.empty(B, D, dtype=out_dtype, device=dev)
-    gate_idx = torch.empty(B, D, dtype=torch.uint8, device=dev) if (want_gate and want_gate_idx) else None
-    rmin = torch.empty(B, dtype=torch.float32, device=dev) if want_minmax else None
-    rmax = torch.empty(B, dtype=torch.float32, device=dev) if want_minmax else None
+        out = torch.empty(*lead, B, D, dtype=out_dtype, device=dev)
+    gate_idx = torch.empty(*lead, B, D, dtype=torch.uint8, device=dev) if (want_gate and want_gate_idx) else None
+    rmin = torch.empty(*lead, B, dtype=torch.float32, device=dev) if want_minmax else None
+    rmax = torch.empty(*lead, B, dtype=torch.float32, device=dev) if want_minmax else None
     bl = blocks + [None] * (3 - len(blocks))
-    args = []
+    args, sx = [], []
     for b in bl:
-        args += [_ptr(b), 0 if b is None else b.shape[1], 0 if b is None else b.stride(0)]
+        args += [_ptr(b), 0 if b is None else b.shape[-1], 0 if b is None else b.stride(-2)]
+        sx.append(0 if b is None or b.dim() == 2 else b.stride(0))
     if lap is not None:
         _chk(lap, torch.float32, "lap")
-        assert lap.is_contiguous() and lap.numel() == B * D
+        assert lap.is_contiguous() and lap.numel() == M * B * D
     if gum is not None:
         _chk(gum, torch.float32, "gum")
-        assert gum.is_contiguous() and gum.numel() == 2 * B * D
+        assert gum.is_contiguous() and gum.numel() == M * 2 * B * D
+    s_coef = 0 if w is None or w.dim() == 1 else w.stride(0)
+    s_out = out.stride(0) if out.dim() == 3 else 0
     L.call("pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
            int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
-           out.stride(0), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), _stream())
+           out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
+           _stream())
     return out, gate_idx, rmin, rmax
 
 
-def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0, row0=0, out=None, accumulate=False):
-    """dDP[D] = deps_dDP * sum_b dF * noise.  Autograd of models.py:75-76."""
+def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0, row0=0, out=None, accumulate=False,
+                        seed_step=0):
+    """dDP = deps_dDP * sum_b dF * noise.  Autograd of models.py:75-76.  dF [B,D] or [M,B,D]."""
     _chk(dF, None, "dF")
-    B, D = dF.shape
+    B, D = dF.shape[-2:]
+    M = 1 if dF.dim() == 2 else dF.shape[0]
     if out is None:
-        out = torch.empty(D, dtype=torch.float32, device=dF.device)
-    nbytes = L.query("pgf_perturb_gate_bwd_dp_workspace", B, D)
+        out = torch.empty((D,) if dF.dim() == 2 else (M, D), dtype=torch.float32, device=dF.device)
+    nbytes = L.query("pgf_perturb_gate_bwd_dp_workspace", B, D, M)
     ws = workspace("perturb_bwd").get(nbytes, dF.device)
-    L.call("pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(0), B, D, noise_mode, _ptr(lap), int(seed),
-           int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), ws.data_ptr(), ws.numel() * 4, out.data_ptr(),
-           int(accumulate), _stream())
+    s_dF = 0 if dF.dim() == 2 else dF.stride(0)
+    s_coef = 0 if deps_dDP.dim() == 1 else deps_dDP.stride(0)
+    s_out = 0 if out.dim() == 1 else out.stride(0)
+    L.call("pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(-2), s_dF, B, D, M, noise_mode, _ptr(lap), int(seed),
+           int(seed_step), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), s_coef, ws.data_ptr(), ws.numel() * 4,
+           out.data_ptr(), s_out, int(accumulate), _stream())
     return out
 
 

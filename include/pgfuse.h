@@ -44,6 +44,7 @@ extern "C" {
 #define PGF_EPI_ATOMIC_F32 4
 #define PGF_EPI_STORE_F32 5
 #define PGF_EPI_BIAS_F32 6
+#define PGF_EPI_BIAS_TANH_F32 7
 
 int pgf_version(void);
 const char* pgf_last_error(void);
@@ -52,11 +53,12 @@ int pgf_num_sms(void);
 /* ---- (a3,a4) per-column privacy coefficients -------------------------------------------------
  * replaces: w = F.sigmoid(self.DP); eps_hat = 1/(((eps.exp()-w)/(1-w)).log())
  *           python/src/custom_models/models.py:73,75 (== past_acc.py:130,132); the unfixed form
- *           (fixed_formula=0) is model.py:57.  `exp_eps` is e^eps already rounded to fp32 by the
- *           host, exactly the scalar that enters `(eps.exp() - w)`.
- * outputs (each [D], any may be NULL): w, eps_hat, deps_dDP = d eps_hat / d DP.              */
-int pgf_dp_coeffs(const float* DP, float exp_eps, int fixed_formula, int D, float* w, float* eps_hat,
-                  float* deps_dDP, void* stream);
+ *           (fixed_formula=0) is model.py:57.  Grouped: DP is [n_models, D] and `exp_eps` a DEVICE
+ *           array [n_models] holding e^eps of each model, already rounded to fp32 by the host --
+ *           exactly the scalar that enters `(eps.exp() - w)`.
+ * outputs (each [n_models, D], any may be NULL): w, eps_hat, deps_dDP = d eps_hat / d DP.       */
+int pgf_dp_coeffs(const float* DP, const float* exp_eps, int fixed_formula, int D, int n_models, float* w,
+                  float* eps_hat, float* deps_dDP, void* stream);
 
 /* ---- (a1,a2,a5,a6,a7) fused concat + row min-max normalise + Laplace perturbation + gate -----
  * replaces: models.py:69-79 (== past_acc.py:120-136): torch.cat, torch.min/max, (x-min)/(max-min),
@@ -69,23 +71,28 @@ int pgf_dp_coeffs(const float* DP, float exp_eps, int fixed_formula, int D, floa
  *            NONE:     out = normalised features.
  * want_gate: evaluate the Gumbel gate (mask applied faithfully in INJECTED mode; in PHILOX mode the
  *            two mask planes sum to one so only the gate index is a real output).
- * out: [B,D] fp32 or bf16 (ld_out); gate_idx [B,D] uint8, row_min/row_max [B]: optional.       */
+ * out: [B,D] fp32 or bf16 (ld_out); gate_idx [B,D] uint8, row_min/row_max [B]: optional.
+ * grouped: n_models launches' worth in one grid; sx* / s_coef / s_out are the model strides of the
+ *          blocks (0 = one batch shared by the whole sweep), of w/eps_hat and of out; lap, gum,
+ *          gate_idx, row_min/max are contiguous per model; model m uses seed + m*seed_step.     */
 int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1,
                          const float* x2, int d2, long long ld2, const float* w, const float* eps_hat, int B,
                          int noise_mode, const float* lap, const float* gum, unsigned long long seed,
                          unsigned int offset, unsigned long long row0, float tau, int hard, int want_gate,
                          void* out, int out_dtype, long long ld_out, unsigned char* gate_idx, float* row_min,
-                         float* row_max, void* stream);
+                         float* row_max, int n_models, long long sx0, long long sx1, long long sx2,
+                         long long s_coef, long long s_out, unsigned long long seed_step, void* stream);
 
 /* ---- (a11) dL/dDP through the perturbation ----------------------------------------------------
  * replaces: autograd through models.py:75-76: dDP[d] = deps_dDP[d] * sum_b dF[b,d] * noise[b,d]
  *           (the gate's own contribution is zero in exact arithmetic).
  * dF: gradient wrt the gated feature [B,D] fp32/bf16.  accumulate!=0 adds into dDP.             */
-size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D);
-int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, int B, int D, int noise_mode,
-                            const float* lap, unsigned long long seed, unsigned int offset,
-                            unsigned long long row0, const float* deps_dDP, float* workspace,
-                            size_t workspace_bytes, float* dDP, int accumulate, void* stream);
+size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D, int n_models);
+int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, long long s_dF, int B, int D, int n_models,
+                            int noise_mode, const float* lap, unsigned long long seed,
+                            unsigned long long seed_step, unsigned int offset, unsigned long long row0,
+                            const float* deps_dDP, long long s_coef, float* workspace, size_t workspace_bytes,
+                            float* dDP, long long s_dDP, int accumulate, void* stream);
 
 /* ---- (a11) gradient wrt the raw feature blocks through the min-max normalisation -------------
  * replaces: autograd through models.py:70-72 (only needed when the encoders are trained).

@@ -16,7 +16,7 @@ Counter / key layout (one Philox call yields the four words of four consecutive 
     word j of the call belongs to column 4*(col//4) + j.
 
 Float transforms (each exact in fp32 before the log):
-    Laplace(0,1):  sign = r>>31, v = (((r>>8) & 0x7FFFFF) + 0.5) * 2^-23,  x = -+log(v)
+    Laplace(0,1):  sign = r>>31, v = ((r & 0x7FFFFF) + 0.5) * 2^-23,  x = -+log(v)
     Gumbel(0,1):   v = ((r>>9) + 0.5) * 2^-23,  E = -log(v) ~ Exp(1),  g = -log(E)
 """
 from __future__ import annotations
@@ -68,7 +68,7 @@ def words(seed: int, offset: int, stream: int, row0: int, B: int, D: int) -> np.
 
 def laplace(seed: int, offset: int, row0: int, B: int, D: int) -> np.ndarray:
     r = words(seed, offset, STREAM_LAPLACE, row0, B, D)
-    v = (((r >> np.uint32(8)) & np.uint32(0x7FFFFF)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+    v = ((r & np.uint32(0x7FFFFF)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
     mag = -np.log(v.astype(np.float64)).astype(np.float32)
     return np.where((r >> np.uint32(31)) != 0, -mag, mag).astype(np.float32)
 

@@ -248,8 +248,6 @@ def test_cls_ce_matches_cal_loss(dev, n_models, B, H):
     from eeg_multimodal_b200 import ops
 
     g = torch.Generator().manual_seed(B + H)
-    for m in range(n_models):
-        pass
     h = torch.tanh(torch.randn(n_models, B, H, generator=g))
     Wc = torch.randn(n_models, 2, H, generator=g) / H ** 0.5
     bc = torch.randn(n_models, 2, generator=g) * 0.1

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks at the BASELINE config-4 shapes (B=65536, D=2560, H=768): CUDA-event
+timings, algorithmic bytes / flops, fraction of the measured peaks.  Inputs are >= 100 MB (larger
+than... or comparable to the 126 MB L2; the big ones are several times L2), `--only` filters by
+name, `--iters` sets the repeat count.  Used for the ncu captures under profiles/."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from eeg_multimodal_b200 import _lib as L, ops  # noqa: E402
+
+
+def timeit(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=65536)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+    B, D, H = a.batch, 2560, 768
+    bf = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(0)
+    x0, x1 = torch.rand(B, 2048, device=dev, generator=g), torch.rand(B, 512, device=dev, generator=g)
+    DP = torch.zeros(D, device=dev)
+    w, eh, deps = ops.dp_coeffs(DP, 2.718281828)
+    Xh = torch.empty(B, D, dtype=bf, device=dev)
+    Xf = torch.empty(B, D, device=dev)
+    W1 = ((torch.rand(D, D, device=dev, generator=g) * 2 - 1) / D ** 0.5).to(bf)
+    W2 = ((torch.rand(H, D, device=dev, generator=g) * 2 - 1) / D ** 0.5).to(bf)
+    b1, b2 = torch.zeros(D, device=dev), torch.zeros(H, device=dev)
+    H1 = torch.empty(B, D, dtype=bf, device=dev)
+    H2 = torch.empty(B, H, device=dev)
+    dZ2 = (torch.randn(B, H, device=dev, generator=g) * 1e-3).to(bf)
+    dZ1 = torch.empty(B, D, dtype=bf, device=dev)
+    dW1, dW2 = torch.zeros(D, D, device=dev), torch.zeros(H, D, device=dev)
+    Wc, bc = torch.randn(2, H, device=dev, generator=g) * 0.03, torch.zeros(2, device=dev)
+    labels = (torch.rand(B, device=dev, generator=g) < 0.66).long()
+    P = D * D + D + H * D + H + 2 * H + 8
+    p, gr, m, v = (torch.zeros(P, device=dev) for _ in range(4))
+    sh = torch.zeros(P, dtype=bf, device=dev)
+    ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh)
+    ops.gemm_bf16(Xh, W1, H1, M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1)
+
+    cases = [
+        ("perturb_fwd_philox_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh), B * D * 6, 0),
+        ("perturb_fwd_philox_f32", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xf), B * D * 8, 0),
+        ("perturb_fwd_nonoise_bf16", lambda: ops.perturb_gate_fwd([x0, x1], None, None, noise_mode=L.NOISE_NONE, out=Xh), B * D * 6, 0),
+        ("perturb_fwd_philox_gate_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh, want_gate=True), B * D * 6, 0),
+        ("perturb_bwd_dp_f32", lambda: ops.perturb_gate_bwd_dp(Xf, deps, noise_mode=L.NOISE_PHILOX, seed=1), B * D * 4, 0),
+        ("perturb_bwd_dp_bf16", lambda: ops.perturb_gate_bwd_dp(Xh, deps, noise_mode=L.NOISE_PHILOX, seed=1), B * D * 2, 0),
+        ("gemm_fwd1", lambda: ops.gemm_bf16(Xh, W1, H1, M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1), 0, 2 * B * D * D),
+        ("gemm_fwd2", lambda: ops.gemm_bf16(H1, W2, H2, M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2), 0, 2 * B * H * D),
+        ("gemm_dZ1", lambda: ops.gemm_bf16(dZ2, W2, dZ1, M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1), 0, 2 * B * H * D),
+        ("gemm_dX", lambda: ops.gemm_bf16(dZ1, W1, Xf, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32), 0, 2 * B * D * D),
+        ("gemm_dW1", lambda: ops.gemm_bf16(dZ1, Xh, dW1, M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True), 0, 2 * B * D * D),
+        ("gemm_dW2", lambda: ops.gemm_bf16(dZ2, H1, dW2, M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True), 0, 2 * B * H * D),
+        ("cls_ce_fwd_bwd", lambda: ops.cls_ce(H2, Wc, bc, labels, loss_scale=1 / B, grad_scale=1 / B, backward=True, dz=dZ2, dz_dtype=bf), B * H * 6, 0),
+        ("colsum_bf16_D", lambda: ops.colsum(dZ1), B * D * 2, 0),
+        ("adam", lambda: ops.adam_step(p, gr, m, v, 1, bf16_shadow=sh), P * 30, 0),
+    ]
+    for name, fn, nbytes, flops in cases:
+        if a.only and a.only not in name:
+            continue
+        ms = timeit(fn, a.iters)
+        line = {"kernel": name, "ms": round(ms, 4)}
+        if nbytes:
+            line["GB/s"] = round(nbytes / ms / 1e6, 1)
+            line["hbm_frac"] = round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 3)
+        if flops:
+            line["TFLOP/s"] = round(flops / ms / 1e9, 1)
+            line["tensor_frac_burst"] = round(flops / ms / 1e9 / peaks["bf16_tflops"], 3)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
