@@ -59,7 +59,7 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     from eeg_multimodal_b200 import _lib
 
     # NULL DP -> argument error before any CUDA call
-    rc = lib.pgf_dp_coeffs(None, 2.7, 1, 16, None, None, None, None)
+    rc = lib.pgf_dp_coeffs(None, None, 1, 16, 1, None, None, None, None)
     assert rc != 0 and b"pgf_dp_coeffs" in lib.pgf_last_error()
     with pytest.raises(RuntimeError, match="pgf_adam_step"):
         _lib.call("pgf_adam_step", None, None, None, None, None, 8, 0, 1e-6, 0.9, 0.999, 1e-8, 1.0, None)
