@@ -160,30 +160,36 @@ __global__ void __launch_bounds__(256) cls_ce_kernel(const CeArgs a) {
 __global__ void cls_ce_finalize_kernel(const float* __restrict__ partial, int nctas, int H, int bwd, float loss_scale,
                                        float B, float* __restrict__ stats, float* __restrict__ dWc, long long sdWc,
                                        float* __restrict__ dbc, long long sdbc) {
+  // thread i owns output i (4 scalars, then 2*H dWc entries): consecutive threads read consecutive
+  // addresses of each CTA's partial row, the loop over CTAs runs in a fixed order (deterministic).
   const int model = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* P = partial + static_cast<long long>(model) * nctas * (2 * H + 4);
   const int stride = 2 * H + 4;
-  if (i < 4) {
-    float s = 0.f;
-    for (int c = 0; c < nctas; ++c) s += P[static_cast<long long>(c) * stride + i];
-    if (i == 0 && stats) stats[model * 4 + 0] = s * loss_scale;
-    if (i == 1 && stats) {
-      stats[model * 4 + 1] = s;
-      stats[model * 4 + 2] = s * loss_scale;
-      stats[model * 4 + 3] = B;
-    }
-    if (bwd && i >= 2 && dbc) dbc[model * sdbc + (i - 2)] = s;
+  const int n_out = bwd ? stride : 4;
+  if (i >= n_out) return;
+  const float* P = partial + static_cast<long long>(model) * nctas * stride + i;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= nctas; c += 4) {
+    s0 += P[static_cast<long long>(c) * stride];
+    s1 += P[static_cast<long long>(c + 1) * stride];
+    s2 += P[static_cast<long long>(c + 2) * stride];
+    s3 += P[static_cast<long long>(c + 3) * stride];
   }
-  if (bwd && dWc && i < 2 * H) {
-    float s = 0.f;
-    for (int c = 0; c < nctas; ++c) s += P[static_cast<long long>(c) * stride + 4 + i];
-    dWc[model * sdWc + i] = s;
+  for (; c < nctas; ++c) s0 += P[static_cast<long long>(c) * stride];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (i == 0 && stats) stats[model * 4 + 0] = s * loss_scale;
+  if (i == 1 && stats) {
+    stats[model * 4 + 1] = s;
+    stats[model * 4 + 2] = s * loss_scale;
+    stats[model * 4 + 3] = B;
   }
+  if (bwd && (i == 2 || i == 3) && dbc) dbc[model * sdbc + (i - 2)] = s;
+  if (bwd && i >= 4 && dWc) dWc[model * sdWc + (i - 4)] = s;
 }
 
 int cls_ce_ctas(int B, int n_models) {
-  int ctas = (2 * num_sms() + n_models - 1) / n_models;
+  int ctas = (num_sms() + n_models - 1) / n_models;
   const int max_ctas = (B + 7) / 8;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
@@ -241,9 +247,9 @@ int cls_ce(const CeArgs& a_in, int h_dtype, int dz_dtype, int bwd, int n_models,
   else if (nv <= 6) rc = launch_ce<6>(a, h_dtype, dz_dtype, bwd != 0, n_models, ctas, s);
   else rc = launch_ce<8>(a, h_dtype, dz_dtype, bwd != 0, n_models, ctas, s);
   if (rc != PGF_OK) return rc;
-  const int n = 2 * a.H > 4 ? 2 * a.H : 4;
-  const dim3 fgrid((n + 255) / 256, n_models);
-  cls_ce_finalize_kernel<<<fgrid, 256, 0, s>>>(workspace, ctas, a.H, bwd, loss_scale, static_cast<float>(a.B), stats, dWc,
+  const int n = 2 * a.H + 4;
+  const dim3 fgrid((n + 127) / 128, n_models);
+  cls_ce_finalize_kernel<<<fgrid, 128, 0, s>>>(workspace, ctas, a.H, bwd, loss_scale, static_cast<float>(a.B), stats, dWc,
                                                sdWc, dbc, sdbc);
   PGF_CUDA_LAUNCH_CHECK("pgf_cls_ce(finalize)");
   return PGF_OK;

@@ -21,6 +21,7 @@
 // (tile, k-block) space is cut into equal contiguous ranges and partial tiles are combined
 // with fp32 vector reductions into a zero-initialised C.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "pgf_kernels.cuh"
 
@@ -35,13 +36,18 @@ namespace pgf {
 #define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
 #define PGF_EPI_BIAS_TANH_F32 7     // C(fp32) = tanh(acc + bias[n])
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;  // BM = accumulator rows per CTA (TMEM lanes)
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-
+// CG = CTAs per MMA (tcgen05 cta_group).  CG=2: a CTA pair (cluster of 2, one TPC) owns a 256x256
+// tile; each CTA stages its own 128 A rows and HALF of the B tile, the MMA reads both halves, so
+// shared-memory fill traffic per flop drops by a third and the ring gets 6 stages instead of 4.
+template <int CG> struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;     // 32 KB (CG=1) / 16 KB (CG=2)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -52,6 +58,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier living in another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -65,22 +89,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// TMA tile load; completes `bytes` on mbarrier `bar`.  CG=2: `bar` is the LEADER CTA's barrier
+// (shared::cluster address), the data lands in the issuing CTA's own shared memory.
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
+// make the mbarrier (same offset in every CTA of the MMA group) track completion of all MMAs issued so far
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -112,20 +165,24 @@ struct WorkUnit {
   int tile, kb0, kb1;
 };
 
+// Work distribution over `nworkers` MMA groups (CTAs or CTA pairs): whole tiles round-robin, or
+// (stream-K) equal contiguous ranges of the flattened (tile, k-block) space.
 struct Scheduler {
-  int num_tiles, kb_total, stream_k;
+  int num_tiles, kb_total, stream_k, worker, nworkers;
   long long cur, end;
   int it;
-  __device__ Scheduler(const GemmArgs& g) {
-    const int mb = (g.M + BM - 1) / BM, nb = (g.N + BN - 1) / BN;
+  __device__ Scheduler(const GemmArgs& g, int tile_m, int worker_, int nworkers_) {
+    const int mb = (g.M + tile_m - 1) / tile_m, nb = (g.N + BN - 1) / BN;
     num_tiles = mb * nb;
     kb_total = (g.K + BK - 1) / BK;
     stream_k = g.stream_k;
+    worker = worker_;
+    nworkers = nworkers_;
     it = 0;
     if (stream_k) {
       const long long total = static_cast<long long>(num_tiles) * kb_total;
-      const long long per = (total + gridDim.x - 1) / gridDim.x;
-      cur = min(total, per * blockIdx.x);
+      const long long per = (total + nworkers - 1) / nworkers;
+      cur = min(total, per * worker);
       end = min(total, cur + per);
     } else {
       cur = end = 0;
@@ -141,7 +198,7 @@ struct Scheduler {
       cur += u.kb1 - u.kb0;
       return true;
     }
-    u.tile = blockIdx.x + it * gridDim.x;
+    u.tile = worker + it * nworkers;
     ++it;
     u.kb0 = 0;
     u.kb1 = kb_total;
@@ -153,9 +210,12 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using C = Cfg<CG>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_STAGE_BYTES = C::A_BYTES;
+  constexpr int TILE_M = BM * CG, BN_CTA = BN / CG;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzle atoms must be 1024-byte aligned
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,69 +228,80 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb_n = (g.N + BN - 1) / BN;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs, owns full/tmem_empty
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, CG);   // one arrival per producer of the group (+ the TMA bytes)
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar + 8 * s, 4 * CG);  // one arrival per epilogue warp of the group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
+    // =============================== TMA producer (every CTA) ===============================
     if (lane == 0) {
-      Scheduler sched(g);
+      Scheduler sched(g, TILE_M, worker, nworkers);
       WorkUnit u;
       uint32_t stage = 0, phase = 0;
       while (sched.next(u)) {
-        const int m0 = (u.tile / nb_n) * BM, n0 = (u.tile % nb_n) * BN;
+        const int m0 = (u.tile / nb_n) * TILE_M + static_cast<int>(rank) * BM;
+        const int n0 = (u.tile % nb_n) * BN + static_cast<int>(rank) * BN_CTA;
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t fb_local = full_bar + 8 * stage;
+          const uint32_t fb = CG == 2 ? mapa_u32(fb_local, 0) : fb_local;  // the leader's barrier
+          if (rank == 0) mbar_expect_tx(fb_local, STAGE_BYTES * CG);
+          else mbar_arrive_cluster(fb);
           const int k0 = kb * BK;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, fb, m0 + 64 * j, k0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d<CG>(sa + j * 8192, &tmA, fb, m0 + 64 * j, k0);
           } else {
-            tma_load_2d(sa, &tmA, fb, k0, m0);
+            tma_load_2d<CG>(sa, &tmA, fb, k0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, fb, n0 + 64 * j, k0);
+            for (int j = 0; j < BN_CTA / 64; ++j) tma_load_2d<CG>(sb + j * 8192, &tmB, fb, n0 + 64 * j, k0);
           } else {
-            tma_load_2d(sb, &tmB, fb, k0, n0);
+            tma_load_2d<CG>(sb, &tmB, fb, k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (leader CTA, one thread) ===============================
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: fp32 accum, bf16 x bf16, majors, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A_MN) << 15) |
                              (static_cast<uint32_t>(B_MN) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                             (static_cast<uint32_t>(BM >> 4) << 24);
-      Scheduler sched(g);
+                             (static_cast<uint32_t>(TILE_M >> 4) << 24);
+      Scheduler sched(g, TILE_M, worker, nworkers);
       WorkUnit u;
       uint32_t stage = 0, phase = 0, unit = 0;
       while (sched.next(u)) {
@@ -248,33 +319,54 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // advance along K: K-major +32 B inside the swizzle atom; MN-major +2 k-groups (2 KB)
             const uint64_t ao = static_cast<uint64_t>((A_MN ? 2048 * k : 32 * k) >> 4);
             const uint64_t bo = static_cast<uint64_t>((B_MN ? 2048 * k : 32 * k) >> 4);
-            umma_bf16(tmem_d, adesc + ao, bdesc + bo, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(tmem_d, adesc + ao, bdesc + bo, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          umma_commit<CG>(empty_bar + 8 * stage);  // frees the smem slot (in every CTA of the group) when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * acc);  // accumulator ready for the epilogue
+        umma_commit<CG>(tfull_bar + 8 * acc);  // accumulator ready for the epilogue warps of the group
         ++unit;
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..5, every CTA) ===============================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
-    Scheduler sched(g);
+    Scheduler sched(g, TILE_M, worker, nworkers);
     WorkUnit u;
     uint32_t unit = 0;
+    const uint32_t tempty_leader = CG == 2 ? mapa_u32(tempty_bar, 0) : tempty_bar;
     while (sched.next(u)) {
       const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
-      const int m0 = (u.tile / nb_n) * BM, n0 = (u.tile % nb_n) * BN;
+      const int m0 = (u.tile / nb_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (u.tile % nb_n) * BN;
       const int m = m0 + row_in_tile;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      // ReLU-mask source (aux) is prefetched one 32-column chunk ahead so its global-load latency
+      // overlaps the TMEM load + math + stores of the current chunk
+      uint4 aux_next[4];
+      const bool has_aux = (g.epi == PGF_EPI_RELUMASK_BF16) && (m < g.M);
+      const __nv_bfloat16* ax_row = static_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(m) * g.ld_aux;
+      if (has_aux) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (n0 + 8 * q < g.N) aux_next[q] = __ldg(reinterpret_cast<const uint4*>(ax_row + n0 + 8 * q));
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n = n0 + c * 32;
         if (n >= g.N) break;  // warp-uniform
+        uint4 aux_cur[4];
+        if (has_aux) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) aux_cur[q] = aux_next[q];
+          if (c + 1 < BN / 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + 32 + 8 * q < g.N) aux_next[q] = __ldg(reinterpret_cast<const uint4*>(ax_row + n + 32 + 8 * q));
+          }
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c * 32, v);
         if (m < g.M) {
@@ -298,17 +390,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
             }
           } else if (g.epi == PGF_EPI_RELUMASK_BF16) {
-            const __nv_bfloat16* ax = static_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(m) * g.ld_aux + n;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (n + i < g.N) {
-                const uint4 q = *reinterpret_cast<const uint4*>(ax + i);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            for (int q = 0; q < 4; ++q) {
+              if (n + 8 * q < g.N) {
+                const uint32_t w[4] = {aux_cur[q].x, aux_cur[q].y, aux_cur[q].z, aux_cur[q].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 h = unpack_bf16x2(w[j]);
-                  f[i + 2 * j] = h.x > 0.f ? f[i + 2 * j] : 0.f;
-                  f[i + 2 * j + 1] = h.y > 0.f ? f[i + 2 * j + 1] : 0.f;
+                  f[8 * q + 2 * j] = h.x > 0.f ? f[8 * q + 2 * j] : 0.f;
+                  f[8 * q + 2 * j + 1] = h.y > 0.f ? f[8 * q + 2 * j + 1] : 0.f;
                 }
               }
             }
@@ -341,15 +431,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+        else mbar_arrive(tempty_bar + 8 * acc);
+      }
       ++unit;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();  // nobody frees TMEM / exits while the peer still needs it
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -408,33 +504,63 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
   rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
   if (rc != PGF_OK) return rc;
-  rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64) : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN);
+  static const bool force_1cta_b = getenv("PGF_GEMM_1CTA") != nullptr;
+  const int cg_b = (!force_1cta_b && g.M > BM) ? 2 : 1;
+  rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64) : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN / cg_b);
   if (rc != PGF_OK) return rc;
 
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  // CTA pairs (cta_group::2) whenever there is at least one full 256-row tile of work per pair
+  static const bool force_1cta = getenv("PGF_GEMM_1CTA") != nullptr;
+  const int cg = (!force_1cta && g.M > BM) ? 2 : 1;
+  const int tile_m = BM * cg;
+  const int tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
   const int kb_total = (g.K + BK - 1) / BK;
-  const int sms = num_sms();
-  int grid;
+  const int workers_max = num_sms() / cg;
+  int workers;
   if (g.stream_k) {
     if (g.epi != PGF_EPI_ATOMIC_F32) {
       set_error("pgf_gemm_bf16: stream-K needs the fp32 reduction epilogue");
       return PGF_ERR_ARG;
     }
     const long long total = static_cast<long long>(tiles) * kb_total;
-    grid = static_cast<int>(total < sms ? total : sms);
+    workers = static_cast<int>(total < workers_max ? total : workers_max);
   } else {
-    grid = tiles < sms ? tiles : sms;
+    workers = tiles < workers_max ? tiles : workers_max;
   }
-#define PGF_GEMM_LAUNCH(AM, BMN)                                                                                       \
-  do {                                                                                                                 \
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);  \
-    gemm_bf16_tc_kernel<AM, BMN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(tmA, tmB, g);                             \
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * cg);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t lerr = cudaSuccess;
+#define PGF_GEMM_LAUNCH(AM, BMN, CGV)                                                                                     \
+  do {                                                                                                                    \
+    cfg.dynamicSmemBytes = Cfg<CGV>::SMEM_BYTES;                                                                          \
+    cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
+                         Cfg<CGV>::SMEM_BYTES);                                                                           \
+    lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, g);                                      \
   } while (0)
-  if (a_mn && b_mn) PGF_GEMM_LAUNCH(true, true);
-  else if (a_mn) PGF_GEMM_LAUNCH(true, false);
-  else if (b_mn) PGF_GEMM_LAUNCH(false, true);
-  else PGF_GEMM_LAUNCH(false, false);
+#define PGF_GEMM_DISPATCH(CGV)                               \
+  do {                                                       \
+    if (a_mn && b_mn) PGF_GEMM_LAUNCH(true, true, CGV);      \
+    else if (a_mn) PGF_GEMM_LAUNCH(true, false, CGV);        \
+    else if (b_mn) PGF_GEMM_LAUNCH(false, true, CGV);        \
+    else PGF_GEMM_LAUNCH(false, false, CGV);                 \
+  } while (0)
+  if (cg == 2) PGF_GEMM_DISPATCH(2);
+  else PGF_GEMM_DISPATCH(1);
+#undef PGF_GEMM_DISPATCH
 #undef PGF_GEMM_LAUNCH
+  if (lerr != cudaSuccess) {
+    set_error("pgf_gemm_bf16: launch failed: %s", cudaGetErrorString(lerr));
+    return PGF_ERR_CUDA;
+  }
   PGF_CUDA_LAUNCH_CHECK("pgf_gemm_bf16");
   return PGF_OK;
 }

@@ -51,7 +51,7 @@ __device__ __forceinline__ float gate_faithful(float f, float w, float g0, float
 constexpr int FWD_THREADS = 128;  // 4 warps share one row: <= 8 float4 per lane, ~64 registers, 32 warps/SM
 
 template <int NV, int NOISE, typename OutT, bool WANT_GATE>
-__global__ void __launch_bounds__(FWD_THREADS) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
   extern __shared__ float4 smem4[];
   __shared__ float s_part[2][FWD_THREADS / 32][3];  // [parity][warp]{min, max, nan-probe}
   float4* s_eps = smem4;                 // [D/4]  eps_hat (Philox mode: pre-multiplied by -ln2)
@@ -84,24 +84,29 @@ __global__ void __launch_bounds__(FWD_THREADS) perturb_gate_fwd_kernel(const Per
   const float* gum = a.gum ? a.gum + model * 2 * BD : nullptr;
   unsigned char* gate_idx = a.gate_idx ? a.gate_idx + model * BD : nullptr;
 
+  // fused concat (models.py:69): which block a lane's k-th float4 comes from does not depend on the
+  // row, so the (base pointer, row stride) pair is selected once, branch-free, outside the row loop
+  const float* pk[NV];
+  long long ldk[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int col = (tid + FWD_THREADS * k) << 2;
+    const bool in1 = col >= a.d[0], in2 = col >= d01;
+    const float* base = in2 ? x2 : (in1 ? x1 : x0);
+    const int off = in2 ? col - d01 : (in1 ? col - a.d[0] : col);
+    pk[k] = base + off;
+    ldk[k] = in2 ? a.ld[2] : (in1 ? a.ld[1] : a.ld[0]);
+  }
+
   int it = 0;
   for (long long row = blockIdx.x; row < a.B; row += gridDim.x, ++it) {
     float4 v[NV];
     float mn = INFINITY, mx = -INFINITY, probe = 0.f;
-    // ---- fused concat load (models.py:69): all loads issued before first use
+    // all loads of the row are issued before first use
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int col = (tid + FWD_THREADS * k) << 2;
-      if (col < a.D) {
-        const float* p;
-        if (col < a.d[0])
-          p = x0 + row * a.ld[0] + col;
-        else if (col < d01)
-          p = x1 + row * a.ld[1] + (col - a.d[0]);
-        else
-          p = x2 + row * a.ld[2] + (col - d01);
-        v[k] = ldg_stream(reinterpret_cast<const float4*>(p));
-      }
+      if (col < a.D) v[k] = ldg_stream(reinterpret_cast<const float4*>(pk[k] + row * ldk[k]));
     }
     // ---- row min / max (models.py:70-71).  torch.min/max propagate NaN while fminf/fmaxf drop it, so
     // a running sum is carried as a NaN probe (NaN in -> NaN out; an inf/-inf mix also gives the NaN
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
   const unsigned long long seed = a.seed + static_cast<unsigned long long>(model) * a.seed_step;
   const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
   const void* dFm = static_cast<const char*>(a.dF) + model * a.s_dF * static_cast<long long>(sizeof(InT));
-  const float* lapm = a.lap ? lapm + static_cast<long long>(model) * a.B * a.D : nullptr;
+  const float* lapm = a.lap ? a.lap + static_cast<long long>(model) * a.B * a.D : nullptr;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int U = 8;
   int r = r0;
@@ -351,7 +356,7 @@ __global__ void perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial
 
 int perturb_bwd_slabs(int B, int D, int n_models) {
   const int col_ctas = (D / 4 + 127) / 128 * (n_models > 0 ? n_models : 1);
-  int slabs = (num_sms() * 4 + col_ctas - 1) / col_ctas;
+  int slabs = (num_sms() * 8 + col_ctas - 1) / col_ctas;  // ~8 CTAs of 128 threads per SM
   const int max_slabs = (B + 31) / 32;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;

@@ -7,6 +7,13 @@
 
 namespace pgf {
 
+// MUFU.LG2 without the denormal-input fix-up sequence (inputs here are >= 2^-24)
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 #define PGF_STREAM_LAPLACE 0u
 #define PGF_STREAM_GUMBEL0 1u
 #define PGF_STREAM_GUMBEL1 2u
@@ -16,8 +23,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint64_t p0 = static_cast<uint64_t>(M0) * c0, p1 = static_cast<uint64_t>(M1) * c2;  // IMAD.WIDE.U32
+    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
     const uint32_t n0 = hi1 ^ c1 ^ k0;
     const uint32_t n2 = hi0 ^ c3 ^ k1;
     c0 = n0;
@@ -34,8 +42,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // x = -+ln(v).  `laplace_scaled_from_bits(r, c)` returns x * eps_hat given c = -ln2 * eps_hat:
 // lg2(v) * c with the sign bit XOR-ed in (5 instructions + 1 MUFU).
 __device__ __forceinline__ float laplace_scaled_from_bits(uint32_t r, float c) {
-  const float v = fmaf(static_cast<float>(r & 0x7FFFFFu), 1.1920928955078125e-07f, 5.9604644775390625e-08f);
-  const float t = __log2f(v) * c;
+  // (m + 0.5) * 2^-23 without an int->float conversion (I2F shares the quarter-rate pipe with MUFU):
+  // 1.m as a float in [1,2), minus (1 - 2^-24); the result (2m+1)*2^-24 is exact.
+  const float v = __uint_as_float(0x3F800000u | (r & 0x7FFFFFu)) - 0.99999994039535522f;
+  const float t = lg2_ftz(v) * c;
   return __uint_as_float(__float_as_uint(t) ^ (r & 0x80000000u));
 }
 __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
@@ -44,7 +54,7 @@ __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
 
 // Gumbel(0,1) = -log(Exp(1)), Exp(1) = -log(v), v=((r>>9)+0.5)*2^-23.
 __device__ __forceinline__ float gumbel_from_bits(uint32_t r) {
-  const float v = (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  const float v = __uint_as_float(0x3F800000u | (r >> 9)) - 0.99999994039535522f;  // ((r>>9)+0.5)*2^-23, exact
   return -__logf(-logf(v));  // accurate inner log: E = -ln(v) can be tiny
 }
 

@@ -266,7 +266,6 @@ def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=
     logits = torch.empty((*lead, B, 2), dtype=torch.float32, device=dev) if want_logits else None
     pred = torch.empty((*lead, B), dtype=torch.int64, device=dev) if want_pred else None
     stats = torch.empty((*lead, 4), dtype=torch.float32, device=dev)
-    dWc = dbc = None
     if backward:
         if dz is None:
             dz = torch.empty(h.shape, dtype=dz_dtype or h.dtype, device=dev)
@@ -282,7 +281,7 @@ def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=
            _ptr(logits), g3(logits), _ptr(pred), g3(pred), stats.data_ptr(), _ptr(dz), 0 if dz is None else _dt(dz),
            0 if dz is None else dz.stride(-2), 0 if dz is None or dz.dim() == 2 else dz.stride(0), _ptr(dWc), g3(dWc),
            _ptr(dbc), g3(dbc), ws.data_ptr(), ws.numel() * 4, _stream())
-    return dict(logits=logits, pred=pred, stats=stats, dz=dz, dWc=dWc, dbc=dbc)
+    return dict(logits=logits, pred=pred, stats=stats, dz=dz, dWc=dWc if backward else None, dbc=dbc if backward else None)
 
 
 def adam_step(p, g, m, v, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, bf16_shadow=None):

@@ -237,3 +237,52 @@ def reference_step_cpu(blocks, label, p: HeadParams, epsilon, hard_noise_on_host
         loss.backward()
         out = (float(loss), float(acc))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# mixed-precision restatement: the same path with the casts the tensor-core kernels make
+# --------------------------------------------------------------------------------------
+def _q(t: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest-even to bf16 and back (what a bf16 store + load does)"""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def head_fwd_bwd_bf16sim(blocks, p: HeadParams, epsilon, lap_noise, fixed: bool = True, grad_scale=None):
+    """models.py:69-82 + cal_loss + autograd, restated with bf16 rounding at exactly the points where
+    the B200 bf16 path stores bf16 (perturbed features X, weights W1/W2, ReLU output H1, dZ2, dZ1);
+    everything else (accumulation, Tanh output H2, logits, loss, dX, all weight gradients) is fp32.
+    The Gumbel gate is the identity (hard) / within 1 ulp (soft), see gumbel_mask, and is skipped.
+    Needed because a ReLU network's gradient is discontinuous in its inputs: rounding X and W to
+    bf16 flips the sign of a fraction p of pre-activations, which moves dZ1 by ~sqrt(p) in Frobenius
+    norm however exact the GEMMs are; against THIS oracle the kernels must agree to the bf16 bar.
+    Returns dict(logits, loss, grads...)."""
+    eps = epsilon if isinstance(epsilon, torch.Tensor) else eps_tensor(epsilon)
+    label = None
+    feature = minmax_normalise(torch.cat(tuple(blocks), dim=1))
+    w = F.sigmoid(p.DP.detach())
+    eps_hat = eps_hat_of(w, eps, fixed)
+    X = _q(feature + lap_noise * eps_hat)
+    W1q, W2q = _q(p.W1.detach()), _q(p.W2.detach())
+    H1 = _q(F.linear(X, W1q, p.b1.detach()).relu())
+    H2 = F.linear(H1, W2q, p.b2.detach()).tanh()
+    logits = F.linear(H2, p.Wc.detach(), p.bc.detach())
+
+    def backward(label):
+        B = logits.shape[0]
+        lab = label.view(-1)
+        gs = (1.0 / B) if grad_scale is None else grad_scale
+        dlogits = (torch.softmax(logits, 1) - F.one_hot(lab, 2).float()) * gs
+        loss = F.cross_entropy(logits, lab)
+        dWc, dbc = dlogits.t() @ H2, dlogits.sum(0)
+        dZ2 = _q((dlogits @ p.Wc.detach()) * (1 - H2 * H2))
+        dW2, db2 = dZ2.t() @ H1, dZ2.sum(0)
+        dZ1 = _q((dZ2 @ W2q) * (H1 > 0))
+        dW1, db1 = dZ1.t() @ X, dZ1.sum(0)
+        dX = dZ1 @ W1q
+        E = eps.exp().to(torch.float32)
+        L = ((E - w) / (1 - w)).log()
+        coef = -(E - 1) * w / (L * L * (E - w)) if fixed else (E - 1) * w / (E - w)
+        dDP = (dX * lap_noise).sum(0, keepdim=True) * coef
+        return dict(loss=loss, dW1=dW1, db1=db1, dW2=dW2, db2=db2, dWc=dWc, dbc=dbc, dDP=dDP)
+
+    return logits, backward
