@@ -235,7 +235,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, CG);   // one arrival per producer of the group (+ the TMA bytes)
+      mbar_init(full_bar + 8 * s, 1);    // the leader's arrive.expect_tx (+ the TMA bytes of every CTA of the group)
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -275,8 +275,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
           const uint32_t fb_local = full_bar + 8 * stage;
           const uint32_t fb = CG == 2 ? mapa_u32(fb_local, 0) : fb_local;  // the leader's barrier
+          // Only the leader arrives (expecting the bytes of the whole group).  The peer needs no arrival of
+          // its own: it refills slot s only after ITS empty[s] fired, i.e. after the MMAs that consumed the
+          // previous contents retired, which is after the leader's previous full[s] phase completed; so its
+          // complete_tx always lands in the phase it belongs to (and a remote arrive.release.cluster per
+          // k-block would serialise the peer's producer on a cluster-scope fence).
           if (rank == 0) mbar_expect_tx(fb_local, STAGE_BYTES * CG);
-          else mbar_arrive_cluster(fb);
           const int k0 = kb * BK;
           if (A_MN) {
 #pragma unroll
