@@ -165,44 +165,35 @@ struct WorkUnit {
   int tile, kb0, kb1;
 };
 
-// Work distribution over `nworkers` MMA groups (CTAs or CTA pairs): whole tiles round-robin, or
-// (stream-K) equal contiguous ranges of the flattened (tile, k-block) space.
+// Work distribution over `nworkers` MMA groups (CTAs or CTA pairs), round-robin over units.
+//   stream_k == 0: a unit is a whole output tile.
+//   stream_k == S: K is cut into S slabs and a unit is (slab, tile), slab-major: the groups that run
+//   concurrently work on the SAME K slab of both operands, so each slab is read from HBM once and
+//   served to the other tiles from L2 (the weight-gradient GEMMs contract over the batch: K = 65,536,
+//   operands 335 MB each, far larger than L2).  Partial tiles are combined by fp32 reductions.
 struct Scheduler {
-  int num_tiles, kb_total, stream_k, worker, nworkers;
-  long long cur, end;
-  int it;
+  int num_tiles, kb_total, nslab, worker, nworkers, it;
   __device__ Scheduler(const GemmArgs& g, int tile_m, int worker_, int nworkers_) {
     const int mb = (g.M + tile_m - 1) / tile_m, nb = (g.N + BN - 1) / BN;
     num_tiles = mb * nb;
     kb_total = (g.K + BK - 1) / BK;
-    stream_k = g.stream_k;
+    nslab = g.stream_k > 0 ? g.stream_k : 1;
     worker = worker_;
     nworkers = nworkers_;
     it = 0;
-    if (stream_k) {
-      const long long total = static_cast<long long>(num_tiles) * kb_total;
-      const long long per = (total + nworkers - 1) / nworkers;
-      cur = min(total, per * worker);
-      end = min(total, cur + per);
-    } else {
-      cur = end = 0;
-    }
   }
   __device__ bool next(WorkUnit& u) {
-    if (stream_k) {
-      if (cur >= end) return false;
-      u.tile = static_cast<int>(cur / kb_total);
-      u.kb0 = static_cast<int>(cur - static_cast<long long>(u.tile) * kb_total);
-      const long long left = end - cur;
-      u.kb1 = static_cast<int>(min(static_cast<long long>(kb_total), u.kb0 + left));
-      cur += u.kb1 - u.kb0;
-      return true;
+    const long long total = static_cast<long long>(num_tiles) * nslab;
+    while (true) {
+      const long long unit = worker + static_cast<long long>(it) * nworkers;
+      ++it;
+      if (unit >= total) return false;
+      const int slab = static_cast<int>(unit / num_tiles);
+      u.tile = static_cast<int>(unit - static_cast<long long>(slab) * num_tiles);
+      u.kb0 = static_cast<int>(static_cast<long long>(kb_total) * slab / nslab);
+      u.kb1 = static_cast<int>(static_cast<long long>(kb_total) * (slab + 1) / nslab);
+      if (u.kb1 > u.kb0) return true;  // more slabs than k-blocks: skip the empty ones (all roles agree)
     }
-    u.tile = worker + it * nworkers;
-    ++it;
-    u.kb0 = 0;
-    u.kb1 = kb_total;
-    return u.tile < num_tiles;
   }
 };
 
@@ -520,16 +511,28 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   const int tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
   const int kb_total = (g.K + BK - 1) / BK;
   const int workers_max = num_sms() / cg;
-  int workers;
+  int workers = tiles < workers_max ? tiles : workers_max;
   if (g.stream_k) {
     if (g.epi != PGF_EPI_ATOMIC_F32) {
-      set_error("pgf_gemm_bf16: stream-K needs the fp32 reduction epilogue");
+      set_error("pgf_gemm_bf16: split-K needs the fp32 reduction epilogue");
       return PGF_ERR_ARG;
     }
-    const long long total = static_cast<long long>(tiles) * kb_total;
-    workers = static_cast<int>(total < workers_max ? total : workers_max);
-  } else {
-    workers = tiles < workers_max ? tiles : workers_max;
+    // number of K slabs: small enough that one slab of both operands stays L2-resident (<= 64 MB),
+    // then whatever minimises waves x (slab length + epilogue) over the candidates
+    const double slab_bytes_per_kb = 2.0 * BK * (static_cast<double>(g.M) + g.N);
+    int s_min = static_cast<int>(slab_bytes_per_kb * kb_total / (64.0 * 1024 * 1024)) + 1;
+    if (s_min > kb_total) s_min = kb_total;
+    int best = s_min;
+    double best_cost = 1e300;
+    for (int S = s_min; S <= s_min + 24 && S <= kb_total; ++S) {
+      const long long units = static_cast<long long>(tiles) * S;
+      const long long waves = (units + workers_max - 1) / workers_max;
+      const double cost = static_cast<double>(waves) * (static_cast<double>(kb_total) / S + 4.0);
+      if (cost < best_cost) { best_cost = cost; best = S; }
+    }
+    g.stream_k = best;
+    const long long units = static_cast<long long>(tiles) * best;
+    workers = static_cast<int>(units < workers_max ? units : workers_max);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(workers * cg);
