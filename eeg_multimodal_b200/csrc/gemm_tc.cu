@@ -45,8 +45,9 @@ template <int CG> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
   static constexpr int B_BYTES = (BN / CG) * BK * 2;     // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CG == 1 ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = CG == 1 ? 3 : 5;
+  static constexpr int EPI_BYTES = 4 * 16384;  // 2 output staging + 2 mask-source staging buffers, [128 rows][128 B] each
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -197,13 +198,23 @@ struct Scheduler {
   }
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// epilogue output: shared -> global through TMA (plain store, or fp32 add-reduction for split-K partials)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
 template <bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
   using C = Cfg<CG>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_STAGE_BYTES = C::A_BYTES;
   constexpr int TILE_M = BM * CG, BN_CTA = BN / CG;
@@ -211,11 +222,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // 128B-swizzle atoms must be 1024-byte aligned
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem slot
+  const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;  // out staging [2][16 KB], mask staging [2][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES + C::EPI_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4..2S+6) aux_full, tmem slot
   const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES), tempty_bar = smem_u32(bars + 2 * STAGES + 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t auxfull_bar = smem_u32(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb_n = (g.N + BN - 1) / BN;
@@ -225,6 +238,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);    // the leader's arrive.expect_tx (+ the TMA bytes of every CTA of the group)
       mbar_init(empty_bar + 8 * s, 1);
@@ -232,6 +246,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, 4 * CG);  // one arrival per epilogue warp of the group
+      mbar_init(auxfull_bar + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -325,51 +340,61 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // =============================== epilogue (warps 2..5, every CTA) ===============================
+    // TMEM -> registers -> (bias / activation / ReLU mask) -> 128B-swizzled shared staging -> TMA store
+    // (or TMA fp32 add-reduction for split-K partials).  The thread <-> accumulator-row mapping of
+    // tcgen05.ld would make direct global stores touch 32 different lines per instruction; staging
+    // through shared memory hands the global traffic to the TMA engine in full 128-byte rows, and the
+    // ReLU-mask source tile arrives the same way (TMA load, one group ahead).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row_in_tile = quarter * 32 + lane;
+    const int row = quarter * 32 + lane;
+    const bool leader_thread = (warp == 2 && lane == 0);
+    const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
+                         g.epi == PGF_EPI_BIAS_TANH_F32;
+    const bool has_bias = g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32 ||
+                          g.epi == PGF_EPI_BIAS_TANH_F32;
+    const bool has_aux = g.epi == PGF_EPI_RELUMASK_BF16;
+    const int GW = out_f32 ? 32 : 64;  // columns per 128-byte staging row
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     Scheduler sched(g, TILE_M, worker, nworkers);
     WorkUnit u;
-    uint32_t unit = 0;
+    uint32_t unit = 0, gcount = 0, aux_issued = 0, aux_used = 0;
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(tempty_bar, 0) : tempty_bar;
     while (sched.next(u)) {
       const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
       const int m0 = (u.tile / nb_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (u.tile % nb_n) * BN;
-      const int m = m0 + row_in_tile;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      // ReLU-mask source (aux) is prefetched one 32-column chunk ahead so its global-load latency
-      // overlaps the TMEM load + math + stores of the current chunk
-      uint4 aux_next[4];
-      const bool has_aux = (g.epi == PGF_EPI_RELUMASK_BF16) && (m < g.M);
-      const __nv_bfloat16* ax_row = static_cast<const __nv_bfloat16*>(g.aux) + static_cast<long long>(m) * g.ld_aux;
-      if (has_aux) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (n0 + 8 * q < g.N) aux_next[q] = __ldg(reinterpret_cast<const uint4*>(ax_row + n0 + 8 * q));
+      if (has_aux && leader_thread) {  // mask tile of the first group
+        const uint32_t b = aux_issued & 1;
+        mbar_expect_tx(auxfull_bar + 8 * b, 16384);
+        tma_load_2d<1>(epi_base + 32768 + b * 16384, &tmAux, auxfull_bar + 8 * b, n0, m0);
       }
+      if (has_aux) ++aux_issued;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= g.N) break;  // warp-uniform
-        uint4 aux_cur[4];
+      for (int n = n0; n < n0 + BN && n < g.N; n += GW) {  // warp-uniform
+        const uint32_t sbuf = epi_base + (gcount & 1) * 16384;
+        // the store issued two groups ago has finished reading this staging buffer
+        if (leader_thread) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        epi_bar_sync();
         if (has_aux) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) aux_cur[q] = aux_next[q];
-          if (c + 1 < BN / 32) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (n + 32 + 8 * q < g.N) aux_next[q] = __ldg(reinterpret_cast<const uint4*>(ax_row + n + 32 + 8 * q));
+          if (n + GW < n0 + BN && n + GW < g.N) {  // prefetch the next group's mask tile
+            if (leader_thread) {
+              const uint32_t b = aux_issued & 1;
+              mbar_expect_tx(auxfull_bar + 8 * b, 16384);
+              tma_load_2d<1>(epi_base + 32768 + b * 16384, &tmAux, auxfull_bar + 8 * b, n + GW, m0);
+            }
+            ++aux_issued;
           }
         }
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        if (m < g.M) {
+        if (out_f32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (n - n0), v);
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32 ||
-              g.epi == PGF_EPI_BIAS_TANH_F32) {
+          if (has_bias) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               if (n + i < g.N) {
@@ -377,52 +402,78 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
               }
             }
-            if (g.epi == PGF_EPI_BIAS_RELU_BF16) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-            } else if (g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_TANH_F32) {
+            if (g.epi == PGF_EPI_BIAS_TANH_F32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
             }
-          } else if (g.epi == PGF_EPI_RELUMASK_BF16) {
+          }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (n + 8 * q < g.N) {
-                const uint32_t w[4] = {aux_cur[q].x, aux_cur[q].y, aux_cur[q].z, aux_cur[q].w};
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t dst = sbuf + row_off + ((static_cast<uint32_t>(c) ^ swz) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * c]), "f"(f[4 * c + 1]),
+                         "f"(f[4 * c + 2]), "f"(f[4 * c + 3])
+                         : "memory");
+          }
+        } else {
+          const uint32_t abuf = epi_base + 32768 + (aux_used & 1) * 16384;
+          if (has_aux) {
+            mbar_wait(auxfull_bar + 8 * (aux_used & 1), (aux_used >> 1) & 1);
+            ++aux_used;
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (n - n0) + 32 * half, v);
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (has_bias) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (n + 32 * half + i < g.N) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n + 32 * half + i));
+                  f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+                }
+              }
+              if (g.epi == PGF_EPI_BIAS_RELU_BF16) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
+              }
+            } else if (has_aux) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t src = abuf + row_off + ((static_cast<uint32_t>(4 * half + c) ^ swz) << 4);
+                uint32_t w[4];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 h = unpack_bf16x2(w[j]);
-                  f[8 * q + 2 * j] = h.x > 0.f ? f[8 * q + 2 * j] : 0.f;
-                  f[8 * q + 2 * j + 1] = h.y > 0.f ? f[8 * q + 2 * j + 1] : 0.f;
+                  f[8 * c + 2 * j] = h.x > 0.f ? f[8 * c + 2 * j] : 0.f;
+                  f[8 * c + 2 * j + 1] = h.y > 0.f ? f[8 * c + 2 * j + 1] : 0.f;
                 }
               }
             }
-          }
-          if (g.epi == PGF_EPI_ATOMIC_F32) {
-            float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              if (n + i < g.N) red_add_v4(cp + i, f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else if (g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 || g.epi == PGF_EPI_BIAS_TANH_F32) {
-            float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + n;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              if (n + i < g.N) *reinterpret_cast<float4*>(cp + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-            __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(g.C) + static_cast<long long>(m) * g.ldc + n;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (n + i < g.N) {
-                uint4 q;
-                q.x = pack_bf16x2(f[i], f[i + 1]);
-                q.y = pack_bf16x2(f[i + 2], f[i + 3]);
-                q.z = pack_bf16x2(f[i + 4], f[i + 5]);
-                q.w = pack_bf16x2(f[i + 6], f[i + 7]);
-                *reinterpret_cast<uint4*>(cp + i) = q;
-              }
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t dst = sbuf + row_off + ((static_cast<uint32_t>(4 * half + c) ^ swz) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(f[8 * c], f[8 * c + 1])),
+                           "r"(pack_bf16x2(f[8 * c + 2], f[8 * c + 3])), "r"(pack_bf16x2(f[8 * c + 4], f[8 * c + 5])),
+                           "r"(pack_bf16x2(f[8 * c + 6], f[8 * c + 7]))
+                           : "memory");
             }
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
+        epi_bar_sync();
+        if (leader_thread) {
+          if (g.epi == PGF_EPI_ATOMIC_F32) tma_reduce_add_2d(&tmC, sbuf, n, m0);
+          else tma_store_2d(&tmC, sbuf, n, m0);  // rows >= M / columns >= N are clipped by the tensor map
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++gcount;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -432,6 +483,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ++unit;
     }
+    if (leader_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all outputs landed before exit
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (CG == 2) cluster_sync_all(); else __syncthreads();  // nobody frees TMEM / exits while the peer still needs it
@@ -463,21 +515,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}
+// 2-D row-major tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}, 128B swizzle
 static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
-                     int box_rows) {
+                     int box_rows, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
     return PGF_ERR_CUDA;
   }
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", static_cast<int>(r), rows, cols, ld);
     return PGF_ERR_CUDA;
@@ -489,13 +541,24 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
               cudaStream_t s) {
   GemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PGF_OK;
-  if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.ldc % 4) ||
+  const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
+                       g.epi == PGF_EPI_BIAS_TANH_F32;
+  if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.ldc % (out_f32 ? 4 : 8)) ||
       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(g.C)) & 15)) {
-    set_error("pgf_gemm_bf16: N, lda, ldb must be multiples of 8, ldc of 4, pointers 16-byte aligned");
+    set_error("pgf_gemm_bf16: N, lda, ldb must be multiples of 8, ldc of 8 (bf16 out) / 4 (fp32 out), pointers 16-byte aligned");
     return PGF_ERR_ARG;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmAux;
   int rc;
+  // output staging rows are 128 bytes: 64 bf16 or 32 fp32 columns x 128 accumulator rows per TMA store
+  rc = make_tmap(&tmC, g.C, g.M, g.N, g.ldc, out_f32 ? 32 : 64, BM, out_f32);
+  if (rc != PGF_OK) return rc;
+  if (g.epi == PGF_EPI_RELUMASK_BF16) {
+    rc = make_tmap(&tmAux, g.aux, g.M, g.N, g.ld_aux, 64, BM);
+    if (rc != PGF_OK) return rc;
+  } else {
+    tmAux = tmC;
+  }
   // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
   rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
   if (rc != PGF_OK) return rc;
@@ -551,7 +614,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     cfg.dynamicSmemBytes = Cfg<CGV>::SMEM_BYTES;                                                                          \
     cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
                          Cfg<CGV>::SMEM_BYTES);                                                                           \
-    lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, g);                                      \
+    lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, tmC, tmAux, g);                                      \
   } while (0)
 #define PGF_GEMM_DISPATCH(CGV)                               \
   do {                                                       \
