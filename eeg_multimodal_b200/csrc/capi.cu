@@ -81,6 +81,7 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   a.D = d0 + d1 + d2;
   a.B = B;
   a.n_models = n_models; a.s_coef = s_coef; a.s_out = s_out; a.seed_step = seed_step;
+  memset(&a.rk, 0, sizeof(a.rk));
   a.w = w; a.eps_hat = eps_hat; a.lap = lap; a.gum = gum;
   a.seed = seed; a.offset = offset; a.row0 = row0;
   a.tau = tau; a.inv_tau = 1.0f / tau; a.hard = hard;

@@ -50,7 +50,7 @@ __device__ __forceinline__ float gate_faithful(float f, float w, float g0, float
 
 constexpr int FWD_THREADS = 128;  // 4 warps share one row: <= 8 float4 per lane, ~64 registers, 32 warps/SM
 
-template <int NV, int NOISE, typename OutT, bool WANT_GATE>
+template <int NV, int NOISE, typename OutT, bool WANT_GATE, bool CONSTKEYS>
 __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const PerturbFwdArgs a) {
   extern __shared__ float4 smem4[];
   __shared__ float s_part[2][FWD_THREADS / 32][3];  // [parity][warp]{min, max, nan-probe}
@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
         } else if (NOISE == PGF_NOISE_PHILOX) {
           const float4 e4 = s_eps[j];
           const float eh[4] = {e4.x, e4.y, e4.z, e4.w};  // = -ln2 * eps_hat
-          const uint4 r = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
+          const uint4 r = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, a.rk)
+                                    : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] += laplace_scaled_from_bits(rb[e], eh[e]);
@@ -211,18 +212,31 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
   }
 }
 
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, int n_models, int B) {
+  // persistent CTAs: exactly one resident wave (SMs x occupancy), each CTA looping over rows
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 4;
+  int gx = (num_sms() * occ) / (n_models > 0 ? n_models : 1);
+  if (gx > B) gx = B;
+  if (gx < 1) gx = 1;
+  return gx;
+}
+
 template <int NV, int NOISE, typename OutT>
 static int launch_fwd_gate(const PerturbFwdArgs& a, bool want_gate, cudaStream_t stream) {
   const size_t smem = (NOISE == PGF_NOISE_NONE) ? 0 : static_cast<size_t>(a.D) * sizeof(float) * (want_gate ? 2 : 1);
-  // persistent CTAs: ~8 per SM in total (register-limited residency), each looping over rows
-  int gx = (num_sms() * 8 + a.n_models - 1) / a.n_models;
-  if (gx > a.B) gx = a.B;
-  if (gx < 1) gx = 1;
-  const dim3 grid(gx, a.n_models);
-  if (want_gate)
-    perturb_gate_fwd_kernel<NV, NOISE, OutT, true><<<grid, FWD_THREADS, smem, stream>>>(a);
-  else
-    perturb_gate_fwd_kernel<NV, NOISE, OutT, false><<<grid, FWD_THREADS, smem, stream>>>(a);
+  const bool constkeys = NOISE == PGF_NOISE_PHILOX && a.n_models == 1 && !want_gate;
+#define PGF_FWD_LAUNCH(GATE, CK)                                                                                  \
+  do {                                                                                                            \
+    auto kern = perturb_gate_fwd_kernel<NV, NOISE, OutT, GATE, CK>;                                               \
+    const dim3 grid(persistent_grid(kern, FWD_THREADS, smem, a.n_models, a.B), a.n_models);                       \
+    kern<<<grid, FWD_THREADS, smem, stream>>>(a);                                                                 \
+  } while (0)
+  if (want_gate) PGF_FWD_LAUNCH(true, false);
+  else if (constkeys) PGF_FWD_LAUNCH(false, (NOISE == PGF_NOISE_PHILOX));
+  else PGF_FWD_LAUNCH(false, false);
+#undef PGF_FWD_LAUNCH
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_fwd");
   return PGF_OK;
 }
@@ -240,13 +254,40 @@ static int launch_fwd_nv(const PerturbFwdArgs& a, int noise, int out_dtype, bool
 #undef PGF_DISPATCH_OUT
 }
 
-int perturb_gate_fwd(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
+static int perturb_gate_fwd_one(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
   const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
   if (nv <= 2) return launch_fwd_nv<2>(a, noise, out_dtype, want_gate, s);
   if (nv <= 5) return launch_fwd_nv<5>(a, noise, out_dtype, want_gate, s);
   if (nv <= 8) return launch_fwd_nv<8>(a, noise, out_dtype, want_gate, s);
   set_error("pgf_perturb_gate_fwd: fused width D=%d exceeds the register-resident limit 4096", a.D);
   return PGF_ERR_UNSUPPORTED;
+}
+
+int perturb_gate_fwd(const PerturbFwdArgs& a_in, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
+  PerturbFwdArgs a = a_in;
+  a.rk = philox_make_keys(a.seed);
+  // Large batches: one launch per model, so the Philox round keys are compile-time-indexed kernel
+  // arguments (constant-bank operands).  Small batches (the B=8 sweep): one grouped launch.
+  const bool split = noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate &&
+                     static_cast<long long>(a.B) * a.D >= (1LL << 22);
+  if (!split) return perturb_gate_fwd_one(a, noise, out_dtype, want_gate, s);
+  const size_t esz = out_dtype == PGF_DT_F32 ? 4 : 2;
+  for (int m = 0; m < a_in.n_models; ++m) {
+    PerturbFwdArgs b = a_in;
+    b.n_models = 1;
+    for (int i = 0; i < 3; ++i)
+      if (b.x[i]) b.x[i] = a_in.x[i] + m * a_in.sx[i];
+    b.w = a_in.w + m * a_in.s_coef;
+    b.eps_hat = a_in.eps_hat + m * a_in.s_coef;
+    b.out = static_cast<char*>(a_in.out) + static_cast<size_t>(m) * a_in.s_out * esz;
+    if (b.row_min) b.row_min = a_in.row_min + static_cast<long long>(m) * a_in.B;
+    if (b.row_max) b.row_max = a_in.row_max + static_cast<long long>(m) * a_in.B;
+    b.seed = a_in.seed + static_cast<unsigned long long>(m) * a_in.seed_step;
+    b.rk = philox_make_keys(b.seed);
+    const int rc = perturb_gate_fwd_one(b, noise, out_dtype, want_gate, s);
+    if (rc != PGF_OK) return rc;
+  }
+  return PGF_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,6 +306,7 @@ struct PerturbBwdArgs {
   unsigned long long seed;
   unsigned long long seed_step;
   int nslab;
+  PhiloxKeys rk;
   unsigned int offset;
   unsigned long long row0;
   int rows_per_slab;
@@ -284,7 +326,7 @@ __device__ __forceinline__ float4 load_in4<__nv_bfloat16>(const void* p, long lo
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-template <int NOISE, typename InT>
+template <int NOISE, typename InT, bool CONSTKEYS>
 __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column index
   const int col = j << 2;
@@ -308,8 +350,10 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
       if (NOISE == PGF_NOISE_INJECTED) {
         l[u] = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r + u) * a.D + col));
       } else {
-        const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
-                                      PGF_STREAM_LAPLACE, a.offset, k0, k1);
+        const uint4 q = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
+                                                     PGF_STREAM_LAPLACE, a.offset, a.rk)
+                                 : philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
+                                                 PGF_STREAM_LAPLACE, a.offset, k0, k1);
         l[u] = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z),
                            laplace_from_bits(q.w));
       }
@@ -328,8 +372,10 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
     if (NOISE == PGF_NOISE_INJECTED) {
       l = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r) * a.D + col));
     } else {
-      const uint4 q = philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
-                                    PGF_STREAM_LAPLACE, a.offset, k0, k1);
+      const uint4 q = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
+                                                   PGF_STREAM_LAPLACE, a.offset, a.rk)
+                               : philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
+                                               PGF_STREAM_LAPLACE, a.offset, k0, k1);
       l = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z), laplace_from_bits(q.w));
     }
     acc.x = fmaf(g.x, l.x, acc.x);
@@ -388,16 +434,22 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
   a.rows_per_slab = (B + slabs - 1) / slabs;
   a.partial = workspace;
   const dim3 grid((D / 4 + 127) / 128, slabs, n_models);
+  a.rk = philox_make_keys(seed);
   if (noise == PGF_NOISE_INJECTED) {
     if (dtype == PGF_DT_F32)
-      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float><<<grid, 128, 0, s>>>(a);
+      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float, false><<<grid, 128, 0, s>>>(a);
     else
-      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16><<<grid, 128, 0, s>>>(a);
+      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
+  } else if (n_models == 1) {
+    if (dtype == PGF_DT_F32)
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, true><<<grid, 128, 0, s>>>(a);
+    else
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, true><<<grid, 128, 0, s>>>(a);
   } else {
     if (dtype == PGF_DT_F32)
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float><<<grid, 128, 0, s>>>(a);
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, false><<<grid, 128, 0, s>>>(a);
     else
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16><<<grid, 128, 0, s>>>(a);
+      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
   const dim3 fgrid((D + 255) / 256, n_models);

@@ -18,23 +18,62 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 #define PGF_STREAM_GUMBEL0 1u
 #define PGF_STREAM_GUMBEL1 2u
 
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1);
+
+// key given as (k0,k1): the key schedule runs on the uniform datapath (used by the grouped launches,
+// where the seed depends on blockIdx)
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = static_cast<uint64_t>(M0) * c0, p1 = static_cast<uint64_t>(M1) * c2;  // IMAD.WIDE.U32
-    const uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
-    const uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
-    const uint32_t n0 = hi1 ^ c1 ^ k0;
-    const uint32_t n2 = hi0 ^ c3 ^ k1;
-    c0 = n0;
-    c1 = lo1;
-    c2 = n2;
-    c3 = lo0;
+    philox_round(c0, c1, c2, c3, k0, k1);
     k0 += W0;
     k1 += W1;
   }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Round keys of one Philox stream (key schedule k + r*W), computed on the HOST and passed inside the
+// kernel-argument struct: indexed with compile-time constants they become constant-bank operands of
+// the XORs, so the per-call key schedule costs no instructions at all.
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+inline PhiloxKeys philox_make_keys(unsigned long long seed) {
+  PhiloxKeys r;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    r.k[2 * i] = k0;
+    r.k[2 * i + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return r;
+}
+
+// one round, pinned to 2 x IMAD.WIDE + 2 x LOP3
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  uint32_t n0, n1, n2, n3;
+  asm("{\n\t.reg .b64 p0, p1;\n\t.reg .b32 h0, l0, h1, l1;\n\t"
+      "mul.wide.u32 p0, %4, 0xD2511F53;\n\t"
+      "mul.wide.u32 p1, %6, 0xCD9E8D57;\n\t"
+      "mov.b64 {l0, h0}, p0;\n\t"
+      "mov.b64 {l1, h1}, p1;\n\t"
+      "xor.b32 h1, h1, %5;\n\t"
+      "xor.b32 %0, h1, %8;\n\t"
+      "mov.b32 %1, l1;\n\t"
+      "xor.b32 h0, h0, %7;\n\t"
+      "xor.b32 %2, h0, %9;\n\t"
+      "mov.b32 %3, l0;\n\t}"
+      : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3)
+      : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(k0), "r"(k1));
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk.k[2 * r], rk.k[2 * r + 1]);
   return make_uint4(c0, c1, c2, c3);
 }
 
