@@ -254,18 +254,19 @@ class HeadEngine:
         return res
 
     # ---- public steps ---------------------------------------------------------------------------
-    def train_step(self, blocks, labels, row0=0, global_batch=None, grad_hook=None):
+    def train_step(self, blocks, labels, row0=0, global_batch=None, grad_hook=None, dp_pass=True):
         """One reference step (past_acc.py:198-212) for every model.  `blocks`: list of [B,Di]
         (shared by all models) or [M,B,Di]; labels int64 [B] / [B,1] (or [M,B]).
         `grad_hook(tensor)` is called on each gradient buffer before its Adam step (data-parallel
         all-reduce).  Returns per-model stats of pass 2: dict(loss[M], acc[M])."""
         labels = self._labels(labels)
         blocks = [b.contiguous() for b in blocks]
-        self._pass(blocks, labels, hard=False, mode="dp", row0=row0, global_batch=global_batch)
-        if grad_hook is not None:
-            grad_hook(self.dDP)
-        self.t_dp += 1
-        ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
+        if dp_pass:   # dp_pass=False reproduces train.py, where the DP pass is commented out (train.py:100-105)
+            self._pass(blocks, labels, hard=False, mode="dp", row0=row0, global_batch=global_batch)
+            if grad_hook is not None:
+                grad_hook(self.dDP)
+            self.t_dp += 1
+            ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
         res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch)
         if grad_hook is not None:
             grad_hook(self.grad)

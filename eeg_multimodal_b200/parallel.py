@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing for the two sharding modes of SURVEY.md section 8e.
+
+* sweep (configs 3, 5): models are independent, so rank r simply owns a slice of the
+  (eps x seed x variant) grid -- no data-path collective; per-model metrics are gathered on the
+  host at epoch end.  The reference runs the same grid as a sequential Python loop
+  (python/src/custom_models/compare_privacy_budget.py:50-62, past_acc.py:255-260).
+* data-parallel (config 4): one model, the batch is split over ranks, gradients are summed with
+  an all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests) before the Adam steps.
+
+Everything here is backend-agnostic host logic (tested with gloo, world size 2, on CPU).
+"""
+from __future__ import annotations
+
+import itertools
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def sweep_grid(eps_list, n_seeds=1, base_seed=980616, variants=(None,)):
+    """The experiment grid as a flat list of dicts, eps-major like the reference's loops
+    (`for epsilon in epsilon_list`), then seeds, then init variants (model_dict/newfrac_* names)."""
+    grid = []
+    for eps, s, v in itertools.product(eps_list, range(n_seeds), variants):
+        grid.append({"eps": float(eps), "seed": base_seed + s, "variant": v})
+    for i, g in enumerate(grid):
+        g["index"] = i
+    return grid
+
+
+def shard_models(n_models: int, world: int, rank: int):
+    """Model index m -> rank m mod world.  Returns this rank's indices."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    return list(range(rank, n_models, world))
+
+
+def batch_slice(global_batch: int, world: int, rank: int):
+    """Contiguous row range [lo, hi) of a global batch for this rank (data-parallel mode).  `lo` is
+    also the Philox row0, so the noise of a sample does not depend on the partitioning."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def init_distributed(backend=None):
+    """env:// rendezvous from RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return int(os.environ.get("RANK", "0")), world
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    kw = {}
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        kw["device_id"] = torch.device("cuda", local)
+    dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def make_allreduce_hook(group=None):
+    """grad_hook for HeadEngine.train_step: sum the gradient buffer over ranks in place.  The
+    engine scales dlogits by 1/global_batch, so the sum IS the gradient of the global mean loss."""
+    def hook(t: torch.Tensor):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return hook
+
+
+def gather_metrics(local: dict, group=None):
+    """Host-side gather of per-model metrics {model_index: value} from all ranks (epoch end)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(local)
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    merged = {}
+    for d in out:
+        merged.update(d)
+    return dict(sorted(merged.items()))

@@ -1,0 +1,107 @@
+"""CPU: host-side logic around the hot path -- epoch records in the reference's format
+(past_acc.py:218-250), the feature cache / loader (data.py:37-45) and the sweep grid."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eeg_multimodal_b200 import feature_cache as fc
+from eeg_multimodal_b200 import parallel, records
+
+# model_dict/newfrac_1.0eps/best_record.txt of the reference, byte for byte (LF line ends)
+REFERENCE_RECORD = ("Epochs: 48\n        | Train Loss:  0.014\n        | Train Accuracy:  0.998\n"
+                    "        | Val Loss:  0.062\n        | Val Accuracy:  0.987\n        | f_1 Score:  0.990\n")
+
+
+def test_record_format_matches_reference_file():
+    assert records.format_record(48, 0.0141, 0.9979, 0.0624, 0.9871, 0.9899) == REFERENCE_RECORD
+
+
+def test_binary_f1_matches_sklearn():
+    from sklearn.metrics import f1_score
+
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 7, 601):
+        pred = (torch.rand(n, generator=g) < 0.6).long()
+        lab = (torch.rand(n, generator=g) < 0.68).long()
+        # the reference passes (prediction, label) -- swapped -- which leaves binary F1 unchanged
+        assert abs(records.binary_f1(pred, lab) - f1_score(pred.numpy(), lab.numpy(), zero_division=0)) < 1e-12
+    assert records.binary_f1(torch.zeros(5), torch.zeros(5)) == 0.0
+
+
+def test_epoch_meter_is_unweighted_mean_over_batches():
+    """past_acc.py:236: sum of per-batch accuracies / number of batches (the 601-row split ends in a
+    1-sample batch which weighs as much as a full one)."""
+    m = records.EpochMeter()
+    for _ in range(75):
+        m.update(0.1, 1.0, torch.ones(8), torch.ones(8))
+    m.update(2.0, 0.0, torch.zeros(1), torch.ones(1))
+    assert abs(m.acc - 75 / 76) < 1e-12 and abs(m.loss - (7.5 + 2.0) / 76) < 1e-12
+    assert abs(m.f1() - 2 * 600 / (2 * 600 + 1)) < 1e-12
+
+
+def test_record_writer_keeps_best_above_half(tmp_path):
+    w = records.RecordWriter(str(tmp_path), "newfrac_1.0eps/")
+    saved = []
+
+    def meters(f1_hits):
+        tr, va = records.EpochMeter(), records.EpochMeter()
+        tr.update(0.5, 0.7)
+        pred = torch.tensor([1] * f1_hits + [0] * (10 - f1_hits))
+        va.update(0.4, f1_hits / 10, pred, torch.ones(10, dtype=torch.long))
+        return tr, va
+
+    assert not w.epoch_end(1, *meters(2), state_dict_fn=lambda: saved.append(1) or {"DP": torch.zeros(1, 4)})  # F1 0.333 <= 0.5
+    assert not os.path.exists(w.best)
+    assert w.epoch_end(2, *meters(8), state_dict_fn=lambda: {"DP": torch.zeros(1, 4)})
+    assert not w.epoch_end(3, *meters(6), state_dict_fn=lambda: {"DP": torch.ones(1, 4)})
+    assert open(w.whole).read().count("Epochs:") == 3
+    assert open(w.best).read().startswith("Epochs: 2\n")
+    assert torch.equal(torch.load(w.ckpt)["DP"], torch.zeros(1, 4))  # torch zip despite the .pickle name
+
+
+def test_feature_cache_roundtrip_and_loader(tmp_path):
+    blocks, labels = fc.synthetic_features(601, dims=(768, 768, 768), seed=3)
+    path = str(tmp_path / "feat.npz")
+    fc.save_features(path, blocks, labels)
+    b2, l2 = fc.load_features(path)
+    assert all(torch.equal(a, b) for a, b in zip(blocks, b2)) and torch.equal(labels, l2)
+    loader = fc.FeatureLoader(b2, l2, batch_size=8, shuffle=True, seed=5, device="cpu")
+    assert len(loader) == 76                       # 75 full batches + the 1-sample tail (kept, like the reference)
+    seen, sizes = [], []
+    for bl, lab in loader:
+        sizes.append(lab.shape[0])
+        seen.append(bl[0][:, 0].clone())
+        assert [b.shape[1] for b in bl] == [768, 768, 768]
+    assert sizes == [8] * 75 + [1]
+    got = torch.sort(torch.cat(seen)).values
+    assert torch.equal(got, torch.sort(blocks[0][:, 0]).values)   # a permutation of the rows
+    first_epoch = torch.cat(seen)
+    second_epoch = torch.cat([bl[0][:, 0].clone() for bl, _ in loader])
+    assert not torch.equal(first_epoch, second_epoch)             # reshuffled every epoch
+    with pytest.raises(ValueError):
+        fc.save_features(path, [np.zeros((3, 4)), np.zeros((2, 4))], np.zeros(3))
+
+
+def test_synthetic_features_follow_survey_8d():
+    blocks, labels = fc.synthetic_features(20000, dims=(2048, 512))
+    assert [tuple(b.shape) for b in blocks] == [(20000, 2048), (20000, 512)]
+    assert 0.0 <= float(blocks[0].min()) and float(blocks[0].max()) < 1.0
+    assert abs(float(labels.float().mean()) - 0.66) < 0.02
+
+
+def test_sweep_grid_and_sharding():
+    grid = parallel.sweep_grid([0.1, 1, 3, 5, 8, 10], n_seeds=8)
+    assert len(grid) == 48 and grid[0]["eps"] == 0.1 and grid[8]["eps"] == 1.0 and grid[1]["seed"] == 980617
+    owned = [parallel.shard_models(48, 8, r) for r in range(8)]
+    assert all(len(o) == 6 for o in owned)
+    assert sorted(sum(owned, [])) == list(range(48))
+    assert parallel.shard_models(5, 8, 7) == []                   # more ranks than models: idle rank
+    with pytest.raises(ValueError):
+        parallel.shard_models(4, 2, 2)
+    for gb, world in ((65536, 8), (601, 4), (7, 8)):
+        cuts = [parallel.batch_slice(gb, world, r) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == gb
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+        assert max(hi - lo for lo, hi in cuts) - min(hi - lo for lo, hi in cuts) <= 1
