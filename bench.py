@@ -39,7 +39,7 @@ BATCH = 65536
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep_synth64k", choices=["sweep_synth64k", "dp64k", "sweep48_b8"])
@@ -59,32 +59,56 @@ def flops_per_sample_step(D, H):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region, through NVML (nvidia_ml_py), every 10 ms."""
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.power, self.reasons, self.stop_flag, self.max_sm = index, [], [], set(), False, None
+        self.err = None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                time.sleep(0.01)
+        except Exception as e:  # no NVML: fall back to polling nvidia-smi (slower, fewer samples)
+            self.err = repr(e)
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(int(out[0]))
+                    self.max_sm = int(out[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.1)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+               "samples": len(sm), "power_w_max": max(self.power) if self.power else None}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peaks():
@@ -92,6 +116,68 @@ def measured_peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def kernel_work(tag):
+    """(kernel name, bound, ALGORITHMIC work per launch) of one timed C-ABI call; bytes for HBM-bound
+    kernels, flops for the tensor-core GEMMs (DESIGN.md section 3 states the per-unit figures)."""
+    kind = tag[0]
+    if kind == "gemm":
+        _, m, n, k, a_mn, b_mn, epi = tag
+        return f"gemm_bf16_tc M={m} N={n} K={k} a_mn={a_mn} b_mn={b_mn} epi={epi}", "tensor", 2.0 * m * n * k
+    if kind == "perturb_fwd":
+        _, b, d, m, dt, noise, gate = tag
+        return f"perturb_gate_fwd B={b} D={d} models={m} out={'f32' if dt == 0 else 'bf16'}", "hbm", float(m) * b * d * (4 + (4 if dt == 0 else 2))
+    if kind == "perturb_bwd_dp":
+        _, b, d, m, dt = tag
+        return f"perturb_bwd_dp B={b} D={d} models={m}", "hbm", float(m) * b * d * (4 if dt == 0 else 2)
+    if kind == "cls_ce":
+        _, b, h, m, dt, bwd = tag
+        hs = 4 if dt == 0 else 2
+        return f"cls_ce B={b} H={h} models={m} bwd={bwd}", "hbm", float(m) * b * (h * hs + (h * 2 if bwd else 0) + 8)
+    if kind == "adam":
+        _, n, shadow = tag
+        return f"adam n={n}", "hbm", float(n) * (28 + (2 if shadow else 0))
+    if kind == "colsum":
+        _, b, n, dt = tag
+        return f"colsum B={b} N={n}", "hbm", float(b) * n * (4 if dt == 0 else 2)
+    if kind == "reduce_partials":
+        return f"reduce_partials rows={tag[1]} N={tag[2]}", "hbm", float(tag[1]) * tag[2] * 4
+    if kind in ("linear_fwd", "linear_bwd_dx", "linear_bwd_dw"):
+        _, b, n, k, m = tag       # weight streaming: one pass over (or one write of) the [N,K] fp32 matrix per model
+        return f"{kind} B={b} N={n} K={k} models={m}", "hbm", float(m) * n * k * 4
+    return str(tag), "hbm", 0.0
+
+
+def kernel_table(timing, total_ms, steps, peaks, peak_kind):
+    """Aggregate the (tag, start, end) events of the timed region.  Returns (table, roofline of the
+    kernel with the largest share of the step)."""
+    if not timing:
+        return None, None
+    agg = {}
+    for tag, a, b in timing:
+        t, n = agg.get(tag, (0.0, 0))
+        agg[tag] = (t + a.elapsed_time(b), n + 1)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        traffic = {}
+    rows = []
+    for tag, (t_ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        name, bound, work = kernel_work(tag)
+        if bound == "tensor":
+            peak, unit, pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "TFLOP/s", "sustained cuBLAS bf16"
+            achieved = work / (t_ms / n * 1e-3) / 1e12
+        else:
+            peak, unit, pk = peaks["hbm_gbs"], "GB/s", "copy bandwidth"
+            achieved = work / (t_ms / n * 1e-3) / 1e9
+        rows.append({"kernel": name, "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": unit,
+                     "frac": round(achieved / peak, 4), "peak_kind": f"{peak_kind} ({pk})", "traffic": traffic.get(name),
+                     "share_of_step": round(t_ms / total_ms, 4), "avg_launch_ms": round(t_ms / n, 4), "launches_per_step": n / steps})
+    timed = sum(v[0] for v in agg.values())
+    top = dict(rows[0])
+    top["timed_kernels_ms_per_step"] = timed / steps
+    return rows, top
 
 
 # --------------------------------------------------------------------------------------------------
@@ -192,7 +278,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     _lib.launch_count = 0
-    ops.GEMM_TIMING = [] if precision == "bf16" else None
+    ops.TIMING = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -200,8 +286,8 @@ def run_ours(args):
     e1.record()
     fence()
     launches = _lib.launch_count
-    gemm_t = ops.GEMM_TIMING
-    ops.GEMM_TIMING = None
+    timing = ops.TIMING
+    ops.TIMING = None
     ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -213,24 +299,12 @@ def run_ours(args):
     samples_per_step = total_models * B * (world if args.workload == "dp64k" else 1)
     value = samples_per_step * K / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (largest share of GEMM time), from the timed region's own events
+    # ---- per-kernel rooflines from the timed region's own CUDA events (every launch is bracketed)
     peaks, peak_kind = measured_peaks()
-    roofline = None
-    if gemm_t:
-        agg = {}
-        for tag, a, b in gemm_t:
-            t, n = agg.get(tag, (0.0, 0))
-            agg[tag] = (t + a.elapsed_time(b), n + 1)
-        tag, (t_ms, n) = max(agg.items(), key=lambda kv: kv[1][0])
-        m_, n_, k_ = tag[:3]
-        achieved = 2.0 * m_ * n_ * k_ / (t_ms / n * 1e-3) / 1e12
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        roofline = {"bound": "tensor", "kernel": f"gemm_bf16_tc M={m_} N={n_} K={k_} a_mn={tag[3]} b_mn={tag[4]} epi={tag[5]}",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_kind": f"{peak_kind} (sustained cuBLAS bf16)", "traffic": None,
-                    "share_of_step": t_ms / ms, "avg_launch_ms": t_ms / n,
-                    "all_gemms_ms_per_step": sum(v[0] for v in agg.values()) / K,
-                    "step_tensor_frac": flops_per_sample_step(D, HIDDEN) * B * M * K / (ms * 1e-3) / 1e12 / peak}
+    kernels, roofline = kernel_table(timing, ms, K, peaks, peak_kind)
+    if roofline is not None and precision == "bf16":
+        roofline["step_tensor_frac"] = flops_per_sample_step(D, HIDDEN) * B * M * K / (ms * 1e-3) / 1e12 / roofline["peak"] \
+            if roofline["bound"] == "tensor" else None
 
     # ---- end to end through the public API: host (pinned) buffers, H2D per step, D2H of the losses
     e2e = None
@@ -292,7 +366,7 @@ def run_ours(args):
                            "feature_dims": list(dims), "hidden": HIDDEN, "eps": eps, "step": "reference two-pass step incl. both Adam updates",
                            "l2": f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)",
                            "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
                 "loss_last": [float(x) for x in st["loss"].cpu()]}
         print(json.dumps(line))
     if world > 1:

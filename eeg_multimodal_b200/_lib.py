@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpgfuse.so")
 DT_F32, DT_BF16 = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32, EPI_BIAS_TANH_F32 = range(8)
+EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32, EPI_BIAS_TANH_F32, EPI_DDP_PARTIAL, EPI_BITMASK_BF16 = range(10)
 
 P, I, LL, F, U32, U64, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint, C.c_ulonglong, C.c_size_t
 
@@ -32,9 +32,12 @@ SIGNATURES = {
     "pgf_linear_bwd_dx_workspace": (SZ, [I, I, I, I]),
     "pgf_linear_bwd_dx": (I, [P, LL, LL, P, LL, P, I, LL, LL, P, LL, LL, I, I, I, I, P, SZ, P]),
     "pgf_linear_bwd_dw": (I, [P, LL, LL, P, LL, LL, P, LL, P, LL, I, I, I, I, I, P]),
-    "pgf_gemm_bf16": (I, [P, LL, I, P, LL, I, P, LL, I, I, I, I, P, P, LL, I, P]),
+    "pgf_gemm_bf16": (I, [P, LL, I, P, LL, I, P, LL, I, I, I, I, P, P, LL, I, P, P]),
+    "pgf_gemm_partial_rows": (I, [I]),
+    "pgf_reduce_partials": (I, [P, I, I, P, P, I, P]),
+    "pgf_gemm_bf16_ddp": (I, [P, LL, P, LL, I, I, I, I, U64, U32, U64, P, P, SZ, P, I, P]),
     "pgf_cls_ce_workspace": (SZ, [I, I, I]),
-    "pgf_cls_ce": (I, [P, I, LL, LL, P, LL, P, LL, P, LL, I, I, I, F, F, I, I, P, LL, P, LL, P, P, I, LL, LL, P, LL, P, LL, P, SZ, P]),
+    "pgf_cls_ce": (I, [P, I, LL, LL, P, LL, P, LL, P, LL, I, I, I, F, F, I, I, P, LL, P, LL, P, P, I, LL, LL, P, LL, P, LL, P, LL, P, SZ, P]),
     "pgf_adam_step": (I, [P, P, P, P, P, LL, I, F, F, F, F, F, P]),
     "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
     "pgf_colsum_workspace": (SZ, [I, I]),
@@ -61,7 +64,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful call (for the bench's `gpu_launches` count)
-LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2}
+LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2}
 launch_count = 0
 launch_by_name = {}
 

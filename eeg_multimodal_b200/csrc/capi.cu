@@ -189,17 +189,39 @@ int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float
 }
 
 int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
-                  int M, int N, int K, int epi, const float* bias, const void* aux, long long ld_aux, int stream_k,
-                  void* stream) {
+                  int M, int N, int K, int epi, const float* bias, void* aux, long long ld_aux, int stream_k,
+                  float* col_partial, void* stream) {
   PGF_CHECK_ARG(A && B && C, "pgf_gemm_bf16: NULL operand");
-  PGF_CHECK_ARG(epi >= 0 && epi <= 7, "pgf_gemm_bf16: bad epilogue %d", epi);
+  PGF_CHECK_ARG((epi >= 0 && epi <= 7) || epi == 9, "pgf_gemm_bf16: bad epilogue %d", epi);
   if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32 || epi == PGF_EPI_BIAS_TANH_F32)
     PGF_CHECK_ARG(bias && aligned16(bias), "pgf_gemm_bf16: epilogue needs a 16-byte aligned bias");
   if (epi == PGF_EPI_RELUMASK_BF16) PGF_CHECK_ARG(aux && aligned16(aux) && (ld_aux % 8) == 0, "pgf_gemm_bf16: epilogue needs aux");
-  GemmArgs g;
+  GemmArgs g = {};
   g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.aux = aux; g.ld_aux = ld_aux; g.epi = epi;
-  g.stream_k = stream_k;
+  g.stream_k = stream_k; g.col_partial = col_partial;
   return gemm_bf16(A, lda, a_mn, B, ldb, b_mn, g, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_gemm_partial_rows(int M) { return gemm_partial_rows(M); }
+
+int pgf_reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate, void* stream) {
+  PGF_CHECK_ARG(partial && out && rows > 0 && N > 0, "pgf_reduce_partials: bad argument");
+  return reduce_partials(partial, rows, N, coef, out, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_gemm_bf16_ddp(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                      unsigned long long seed, unsigned int offset, unsigned long long row0, const float* deps_dDP,
+                      float* workspace, size_t workspace_bytes, float* dDP, int accumulate, void* stream) {
+  PGF_CHECK_ARG(A && B && deps_dDP && dDP && workspace, "pgf_gemm_bf16_ddp: NULL argument");
+  PGF_CHECK_ARG(M > 0 && N > 0 && K > 0, "pgf_gemm_bf16_ddp: empty problem");
+  const int rows = gemm_partial_rows(M);
+  PGF_CHECK_ARG(workspace_bytes >= static_cast<size_t>(rows) * N * sizeof(float), "pgf_gemm_bf16_ddp: workspace too small");
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K; g.C = workspace; g.ldc = N; g.epi = 8 /* PGF_EPI_DDP_PARTIAL */;
+  g.col_partial = workspace; g.seed = seed; g.offset = offset; g.row0 = row0;
+  const int rc = gemm_bf16(A, lda, 0, B, ldb, b_mn, g, static_cast<cudaStream_t>(stream));
+  if (rc != PGF_OK) return rc;
+  return reduce_partials(workspace, rows, N, deps_dDP, dDP, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 size_t pgf_cls_ce_workspace(int B, int H, int n_models) {
@@ -211,7 +233,8 @@ int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const fl
                long long sbc, const long long* labels, long long slabels, int B, int H, int n_models, float loss_scale,
                float grad_scale, int backward, int through_tanh, float* logits, long long slogits, long long* pred,
                long long spred, float* stats, void* dz, int dz_dtype, long long lddz, long long sdz, float* dWc,
-               long long sdWc, float* dbc, long long sdbc, float* workspace, size_t workspace_bytes, void* stream) {
+               long long sdWc, float* dbc, long long sdbc, float* dz_colsum, long long sdz_colsum, float* workspace,
+               size_t workspace_bytes, void* stream) {
   if (n_models == 0) return PGF_OK;
   PGF_CHECK_ARG(B > 0, "pgf_cls_ce: empty batch (the reference divides by B: cross_entropy mean over 0 rows is NaN)");
   PGF_CHECK_ARG(h && Wc && bc && workspace, "pgf_cls_ce: NULL argument");
@@ -223,8 +246,9 @@ int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const fl
   a.h = h; a.ldh = ldh; a.sh = sh; a.Wc = Wc; a.sWc = sWc; a.bc = bc; a.sbc = sbc; a.labels = labels; a.slab = slabels;
   a.logits = logits; a.slogits = slogits; a.pred = pred; a.spred = spred; a.dz = dz; a.lddz = lddz; a.sdz = sdz;
   a.partial = workspace; a.B = B; a.H = H; a.grad_scale = grad_scale; a.through_tanh = through_tanh;
-  return cls_ce(a, h_dtype, dz_dtype, backward, n_models, loss_scale, stats, dWc, sdWc, dbc, sdbc, workspace, workspace_bytes,
-                static_cast<cudaStream_t>(stream));
+  PGF_CHECK_ARG(!dz_colsum || (backward && dz), "pgf_cls_ce: dz_colsum needs backward and dz");
+  return cls_ce(a, h_dtype, dz_dtype, backward, n_models, loss_scale, stats, dWc, sdWc, dbc, sdbc, dz_colsum, sdz_colsum,
+                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int pgf_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step, float lr,

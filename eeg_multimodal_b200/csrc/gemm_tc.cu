@@ -35,6 +35,8 @@ namespace pgf {
 #define PGF_EPI_STORE_F32 5         // C(fp32) = acc
 #define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
 #define PGF_EPI_BIAS_TANH_F32 7     // C(fp32) = tanh(acc + bias[n])
+#define PGF_EPI_DDP_PARTIAL 8       // no C: col_partial[m/128][n] = sum over 128 rows of acc * Laplace(row, n)
+#define PGF_EPI_BITMASK_BF16 9      // C = acc * bit(aux, m, n)          (aux uint32 [M, N/32]: ReLU sign bits written by epi 1)
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;  // BM = accumulator rows per CTA (TMEM lanes)
 constexpr int GEMM_THREADS = 192;
@@ -47,7 +49,8 @@ template <int CG> struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = CG == 1 ? 3 : 5;
   static constexpr int EPI_BYTES = 4 * 16384;  // 2 output staging + 2 mask-source staging buffers, [128 rows][128 B] each
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int CS_BYTES = 1024;        // per-warp column sums of one 64-column group, [4 warps][64]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CS_BYTES;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -162,6 +165,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Column sums across the 32 lanes of a warp for 32 per-lane values (lane = accumulator row, f[i] = column i):
+// a 5-step butterfly that halves the number of live values per step (16+8+4+2+1 = 31 shuffles).  Returns, on
+// lane l, the sum over the warp's 32 rows of column l.  f is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? f[i] : f[i + o];
+      const float keep = up ? f[i + o] : f[i];
+      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return f[0];
+}
+
 struct WorkUnit {
   int tile, kb0, kb1;
 };
@@ -229,6 +249,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES), tempty_bar = smem_u32(bars + 2 * STAGES + 2);
   const uint32_t auxfull_bar = smem_u32(bars + 2 * STAGES + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  float* s_cs = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES + C::EPI_BYTES + 256);  // [4][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb_n = (g.N + BN - 1) / BN;
@@ -353,6 +374,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool has_bias = g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32 ||
                           g.epi == PGF_EPI_BIAS_TANH_F32;
     const bool has_aux = g.epi == PGF_EPI_RELUMASK_BF16;
+    // ReLU sign bits, one uint32 per (row, 32 columns): written by the forward epilogue, read back by the
+    // backward one -- 1/16 of the bytes of the bf16 activation tile the mask would otherwise be derived from
+    const bool mask_out = g.epi == PGF_EPI_BIAS_RELU_BF16 && g.aux != nullptr;
+    const bool mask_in = g.epi == PGF_EPI_BITMASK_BF16;
+    uint32_t* mask_words = static_cast<uint32_t*>(const_cast<void*>(g.aux));
+    const bool want_cs = g.col_partial != nullptr && !out_f32;
     const int GW = out_f32 ? 32 : 64;  // columns per 128-byte staging row
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
@@ -363,9 +390,48 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     while (sched.next(u)) {
       const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
       const int m0 = (u.tile / nb_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (u.tile % nb_n) * BN;
+      uint4 mwa = make_uint4(0u, 0u, 0u, 0u), mwb = make_uint4(0u, 0u, 0u, 0u);
+      if (mask_in && m0 + row < g.M) {  // this row's 256 sign bits of the tile: issued before the accumulator wait
+        const uint4* mp = reinterpret_cast<const uint4*>(mask_words + static_cast<long long>(m0 + row) * g.ld_aux + (n0 >> 5));
+        mwa = __ldg(mp);
+        if (n0 + 128 < g.N) mwb = __ldg(mp + 1);
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (g.epi == PGF_EPI_DDP_PARTIAL) {
+        // dX tile never leaves the SM: multiply by the regenerated Laplace noise of (global row, column) and
+        // reduce over the 128 accumulator rows; one 1 KB row of column partials per (128-row slab, N tile).
+        float* cs = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES) + (unit & 1) * (4 * BN);  // [4 warps][256]
+        const uint32_t grow = static_cast<uint32_t>(g.row0 + static_cast<unsigned long long>(m0 + row));
+#pragma unroll 1
+        for (int n = n0; n < n0 + BN && n < g.N; n += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (n - n0), v);
+          float f[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 r = philox4x32_10_rk(static_cast<uint32_t>((n >> 2) + q), grow, PGF_STREAM_LAPLACE, g.offset, g.rk);
+            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) * laplace_from_bits(r.x);
+            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) * laplace_from_bits(r.y);
+            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * laplace_from_bits(r.z);
+            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * laplace_from_bits(r.w);
+          }
+          cs[quarter * BN + (n - n0) + lane] = warp_colsum32(f, lane);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // accumulator fully read: hand TMEM back early
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+          else mbar_arrive(tempty_bar + 8 * acc);
+        }
+        epi_bar_sync();  // one barrier per tile: `cs` is double-buffered on the tile parity
+        float* dst = g.col_partial + static_cast<long long>(m0 / BM) * g.N + n0;
+        for (int c = row; c < BN && n0 + c < g.N; c += 128)
+          dst[c] = (cs[c] + cs[BN + c]) + (cs[2 * BN + c] + cs[3 * BN + c]);
+        ++unit;
+        continue;
+      }
       if (has_aux && leader_thread) {  // mask tile of the first group
         const uint32_t b = aux_issued & 1;
         mbar_expect_tx(auxfull_bar + 8 * b, 16384);
@@ -388,6 +454,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ++aux_issued;
           }
         }
+        uint32_t mw[2] = {0u, 0u};
         if (out_f32) {
           uint32_t v[32];
           tmem_ld32(taddr + (n - n0), v);
@@ -416,6 +483,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         } else {
           const uint32_t abuf = epi_base + 32768 + (aux_used & 1) * 16384;
+          if (mask_in) {
+            const int gi = (n - n0) >> 6;  // 64-column group inside the tile
+            mw[0] = gi == 0 ? mwa.x : (gi == 1 ? mwa.z : (gi == 2 ? mwb.x : mwb.z));
+            mw[1] = gi == 0 ? mwa.y : (gi == 1 ? mwa.w : (gi == 2 ? mwb.y : mwb.w));
+          }
           if (has_aux) {
             mbar_wait(auxfull_bar + 8 * (aux_used & 1), (aux_used >> 1) & 1);
             ++aux_used;
@@ -438,10 +510,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (g.epi == PGF_EPI_BIAS_RELU_BF16) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                if (mask_out) {
+                  uint32_t m = 0u;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) m |= (f[i] > 0.f ? 1u : 0u) << i;
+                  mw[half] = m;
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = tanhf(f[i]);
               }
+            } else if (mask_in) {
+              const uint32_t m = mw[half];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = (m & (1u << i)) ? f[i] : 0.f;
             } else if (has_aux) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -464,8 +546,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            "r"(pack_bf16x2(f[8 * c + 6], f[8 * c + 7]))
                            : "memory");
             }
+            // fused bias gradient: column sums of the (fp32) epilogue values over this warp's 32 rows
+            if (want_cs) s_cs[quarter * 64 + 32 * half + lane] = warp_colsum32(f, lane);
           }
         }
+        if (mask_out && m0 + row < g.M && n < g.N)
+          *reinterpret_cast<uint2*>(mask_words + static_cast<long long>(m0 + row) * g.ld_aux + (n >> 5)) = make_uint2(mw[0], mw[1]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
         epi_bar_sync();
         if (leader_thread) {
@@ -473,6 +559,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else tma_store_2d(&tmC, sbuf, n, m0);  // rows >= M / columns >= N are clipped by the tensor map
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        // combine the 4 warps' column sums of this group (the next group's s_cs writes come after its first barrier)
+        if (want_cs && row < 64 && n + row < g.N)
+          g.col_partial[static_cast<long long>(m0 / BM) * g.N + n + row] =
+              (s_cs[row] + s_cs[64 + row]) + (s_cs[128 + row] + s_cs[192 + row]);
         ++gcount;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -543,7 +633,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PGF_OK;
   const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
                        g.epi == PGF_EPI_BIAS_TANH_F32;
-  if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.ldc % (out_f32 ? 4 : 8)) ||
+  if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.epi != PGF_EPI_DDP_PARTIAL && (g.ldc % (out_f32 ? 4 : 8))) ||
       ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(g.C)) & 15)) {
     set_error("pgf_gemm_bf16: N, lda, ldb must be multiples of 8, ldc of 8 (bf16 out) / 4 (fp32 out), pointers 16-byte aligned");
     return PGF_ERR_ARG;
@@ -551,17 +641,38 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   CUtensorMap tmA, tmB, tmC, tmAux;
   int rc;
   // output staging rows are 128 bytes: 64 bf16 or 32 fp32 columns x 128 accumulator rows per TMA store
-  rc = make_tmap(&tmC, g.C, g.M, g.N, g.ldc, out_f32 ? 32 : 64, BM, out_f32);
+  const bool no_c = g.epi == PGF_EPI_DDP_PARTIAL;
+  if (no_c) {
+    if (!g.col_partial || g.stream_k) {
+      set_error("pgf_gemm_bf16: the dDP epilogue needs the column-partial workspace and no split-K");
+      return PGF_ERR_ARG;
+    }
+    g.rk = philox_make_keys(g.seed);
+  } else if (g.col_partial && out_f32) {
+    set_error("pgf_gemm_bf16: column partials are fused into the bf16-output epilogues only");
+    return PGF_ERR_ARG;
+  }
+  if (g.epi == PGF_EPI_BITMASK_BF16 || (g.epi == PGF_EPI_BIAS_RELU_BF16 && g.aux)) {
+    if (!g.aux || (g.N % 128) || (g.ld_aux % 4) || (reinterpret_cast<uintptr_t>(g.aux) & 15) || g.ld_aux * 32 < g.N) {
+      set_error("pgf_gemm_bf16: the ReLU bitmask needs N %% 128 == 0, a 16-byte aligned uint32 [M, ld_aux >= N/32] buffer, ld_aux %% 4 == 0");
+      return PGF_ERR_ARG;
+    }
+  }
+  // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
+  rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
   if (rc != PGF_OK) return rc;
+  if (no_c) {
+    tmC = tmA;  // never dereferenced
+  } else {
+    rc = make_tmap(&tmC, g.C, g.M, g.N, g.ldc, out_f32 ? 32 : 64, BM, out_f32);
+    if (rc != PGF_OK) return rc;
+  }
   if (g.epi == PGF_EPI_RELUMASK_BF16) {
     rc = make_tmap(&tmAux, g.aux, g.M, g.N, g.ld_aux, 64, BM);
     if (rc != PGF_OK) return rc;
   } else {
     tmAux = tmC;
   }
-  // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
-  rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
-  if (rc != PGF_OK) return rc;
   static const bool force_1cta_b = getenv("PGF_GEMM_1CTA") != nullptr;
   const int cg_b = (!force_1cta_b && g.M > BM) ? 2 : 1;
   rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64) : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN / cg_b);
@@ -633,6 +744,15 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_gemm_bf16");
   return PGF_OK;
+}
+
+// rows of the column-partial workspace for an M-row output: one per 128-row accumulator slab that a CTA owns
+int gemm_partial_rows(int M) {
+  if (M <= 0) return 0;
+  static const bool force_1cta = getenv("PGF_GEMM_1CTA") != nullptr;
+  const int cg = (!force_1cta && M > BM) ? 2 : 1;
+  const int tile_m = BM * cg;
+  return ((M + tile_m - 1) / tile_m) * cg;
 }
 
 }  // namespace pgf

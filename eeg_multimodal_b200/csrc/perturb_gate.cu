@@ -11,6 +11,8 @@
 // per-column coefficients (eps_hat, w) are staged once per CTA in shared memory.
 //
 // HBM traffic per row (Philox mode): read 4*D, write 4*D (fp32 out) or 2*D (bf16 out).
+#include <stdlib.h>
+
 #include "pgf_kernels.cuh"
 #include "philox.cuh"
 
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (NOISE == PGF_NOISE_PHILOX)
-            f[e] = __fmul_rn(__fsub_rn(f[e], mn), inv_range);
+            f[e] = __fsub_rn(f[e], mn);  // scaled by 1/range inside the fused multiply-add below
           else
             f[e] = __fdiv_rn(__fsub_rn(f[e], mn), range);
         }
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
                                     : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) f[e] += laplace_scaled_from_bits(rb[e], eh[e]);
+          for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(f[e], inv_range, laplace_scaled_from_bits(rb[e], eh[e]));
           if (WANT_GATE) {
             // The two mask planes sum to one (hard: exactly, soft: within 1 ulp), so the gated
             // value IS the perturbed value; only the gate index is a real output.
@@ -210,6 +212,180 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Large-batch production variant (Philox / non-private, one model per launch): the CTA's rows arrive
+// through a ring of shared-memory row buffers filled by 1-D bulk async copies (TMA engine,
+// cp.async.bulk + mbarrier complete_tx), RING_STAGES-1 rows ahead of the arithmetic.  Register-side
+// prefetching does not work here: the consumer's wait is a scoreboard wait, and the scoreboard of the
+// row being consumed also covers the just-issued loads of the next row (ncu: 30 % of all stall samples on
+// the first use of the row).  mbarrier completion has no such aliasing, costs no registers, and one elected
+// thread issues the copies, so the other 127 never compute a global address.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ring_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+template <int NV, int NOISE, typename OutT, bool CONSTKEYS, int RING_STAGES>
+__global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_kernel(const PerturbFwdArgs a) {
+  extern __shared__ float4 smem4[];
+  __shared__ float s_part[2][FWD_THREADS / 32][3];
+  __shared__ __align__(8) unsigned long long s_full[RING_STAGES];
+  const int nvec = a.D >> 2;
+  float4* s_eps = smem4;                                   // [D/4]  -ln2 * eps_hat
+  float4* s_rows = smem4 + (NOISE == PGF_NOISE_NONE ? 0 : nvec);  // [RING_STAGES][D/4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < RING_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (NOISE != PGF_NOISE_NONE) {
+    const float4* ge = reinterpret_cast<const float4*>(a.eps_hat);
+    for (int i = tid; i < nvec; i += FWD_THREADS) {
+      float4 e = ge[i];
+      e.x *= -0.69314718055994531f; e.y *= -0.69314718055994531f;
+      e.z *= -0.69314718055994531f; e.w *= -0.69314718055994531f;
+      s_eps[i] = e;
+    }
+  }
+  __syncthreads();
+  const unsigned int k0 = static_cast<unsigned int>(a.seed), k1 = static_cast<unsigned int>(a.seed >> 32);
+  const uint32_t row_bytes = static_cast<uint32_t>(a.D) * 4u;
+
+  // producer (thread 0): one bulk copy per feature block = the fused concat (models.py:69)
+  auto issue = [&](int it) {
+    const long long row = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
+    if (row >= a.B) return;
+    const int st = it % RING_STAGES;
+    const uint32_t bar = smem_addr_u32(&s_full[st]);
+    const uint32_t dst = smem_addr_u32(s_rows + st * nvec);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+    uint32_t off = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (a.d[b] > 0) {
+        const float* src = a.x[b] + row * a.ld[b];
+        const uint32_t nbytes = static_cast<uint32_t>(a.d[b]) * 4u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(src), "r"(nbytes), "r"(bar)
+                     : "memory");
+        off += nbytes;
+      }
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int it = 0; it < RING_STAGES - 1; ++it) issue(it);
+  }
+
+  int it = 0;
+  for (long long row = blockIdx.x; row < a.B; row += gridDim.x, ++it) {
+    const int st = it % RING_STAGES;
+    ring_mbar_wait(smem_addr_u32(&s_full[st]), static_cast<uint32_t>(it / RING_STAGES) & 1u);
+    float4 v[NV];
+    float mn = INFINITY, mx = -INFINITY, probe = 0.f;
+    const float4* srow = s_rows + st * nvec;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = tid + FWD_THREADS * k;
+      if (j < nvec) {
+        v[k] = srow[j];
+        mn = fminf(fminf(mn, v[k].x), fminf(v[k].y, fminf(v[k].z, v[k].w)));
+        mx = fmaxf(fmaxf(mx, v[k].x), fmaxf(v[k].y, fmaxf(v[k].z, v[k].w)));
+        probe += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    probe = warp_sum(probe);
+    float(*part)[3] = s_part[it & 1];
+    if (lane == 0) {
+      part[warp][0] = mn;
+      part[warp][1] = mx;
+      part[warp][2] = probe;
+    }
+    __syncthreads();  // every thread holds its part of row `it` in registers: the previous row's buffer is free
+    if (tid == 0) issue(it + RING_STAGES - 1);
+#pragma unroll
+    for (int w = 0; w < FWD_THREADS / 32; ++w) {
+      mn = fminf(mn, part[w][0]);
+      mx = fmaxf(mx, part[w][1]);
+    }
+    probe = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
+    if (probe != probe) mn = mx = __int_as_float(0x7fc00000);
+    const float range = __fsub_rn(mx, mn);
+    const float inv_range = __frcp_rn(range);
+    if (tid == 0) {
+      if (a.row_min) a.row_min[row] = mn;
+      if (a.row_max) a.row_max[row] = mx;
+    }
+    const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = tid + FWD_THREADS * k;
+      if (j < nvec) {
+        float f[4] = {__fsub_rn(v[k].x, mn), __fsub_rn(v[k].y, mn), __fsub_rn(v[k].z, mn), __fsub_rn(v[k].w, mn)};
+        if (NOISE == PGF_NOISE_PHILOX) {
+          const float4 e4 = s_eps[j];
+          const float eh[4] = {e4.x, e4.y, e4.z, e4.w};  // = -ln2 * eps_hat
+          const uint4 r = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, a.rk)
+                                    : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
+          const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(f[e], inv_range, laplace_scaled_from_bits(rb[e], eh[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[e] = __fdiv_rn(f[e], range);
+        }
+        store_out4<OutT>(a.out, row * a.ld_out + (j << 2), make_float4(f[0], f[1], f[2], f[3]));
+      }
+    }
+  }
+}
+
+template <int NV, int NOISE, typename OutT, int RING_STAGES>
+static int launch_fwd_ring_s(const PerturbFwdArgs& a, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(a.D) * sizeof(float) * (RING_STAGES + (NOISE == PGF_NOISE_NONE ? 0 : 1));
+  auto kern = perturb_fwd_ring_kernel<NV, NOISE, OutT, true, RING_STAGES>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FWD_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+  int gx = num_sms() * occ;
+  if (gx > a.B) gx = a.B;
+  kern<<<gx, FWD_THREADS, smem, stream>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_fwd(ring)");
+  return PGF_OK;
+}
+
+template <int NV, int NOISE, typename OutT>
+static int launch_fwd_ring(const PerturbFwdArgs& a, cudaStream_t stream) {
+  static const char* env = getenv("PGF_RING_STAGES");  // tuning knob: rows in flight per CTA = stages - 1
+  if (env && env[0] == '4') return launch_fwd_ring_s<NV, NOISE, OutT, 4>(a, stream);
+  return launch_fwd_ring_s<NV, NOISE, OutT, 3>(a, stream);
+}
+
+template <int NV>
+static int launch_fwd_ring_nv(const PerturbFwdArgs& a, int noise, int out_dtype, cudaStream_t s) {
+  if (noise == PGF_NOISE_PHILOX)
+    return out_dtype == PGF_DT_F32 ? launch_fwd_ring<NV, PGF_NOISE_PHILOX, float>(a, s)
+                                   : launch_fwd_ring<NV, PGF_NOISE_PHILOX, __nv_bfloat16>(a, s);
+  return out_dtype == PGF_DT_F32 ? launch_fwd_ring<NV, PGF_NOISE_NONE, float>(a, s)
+                                 : launch_fwd_ring<NV, PGF_NOISE_NONE, __nv_bfloat16>(a, s);
 }
 
 template <typename K>
@@ -256,6 +432,12 @@ static int launch_fwd_nv(const PerturbFwdArgs& a, int noise, int out_dtype, bool
 
 static int perturb_gate_fwd_one(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
   const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
+  static const bool no_ring = getenv("PGF_PERTURB_NO_RING") != nullptr;
+  if (!no_ring && noise != PGF_NOISE_INJECTED && !want_gate && a.n_models == 1 && static_cast<long long>(a.B) * a.D >= (1LL << 22)) {
+    if (nv <= 2) return launch_fwd_ring_nv<2>(a, noise, out_dtype, s);
+    if (nv <= 5) return launch_fwd_ring_nv<5>(a, noise, out_dtype, s);
+    if (nv <= 8) return launch_fwd_ring_nv<8>(a, noise, out_dtype, s);
+  }
   if (nv <= 2) return launch_fwd_nv<2>(a, noise, out_dtype, want_gate, s);
   if (nv <= 5) return launch_fwd_nv<5>(a, noise, out_dtype, want_gate, s);
   if (nv <= 8) return launch_fwd_nv<8>(a, noise, out_dtype, want_gate, s);
@@ -386,18 +568,44 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
   *reinterpret_cast<float4*>(a.partial + (static_cast<long long>(model) * a.nslab + slab) * a.D + col) = acc;
 }
 
-__global__ void perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
-                                               const float* __restrict__ coef, long long s_coef,
-                                               float* __restrict__ dDP, long long s_dDP, float accumulate) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+// Deterministic column reduction of a [nslab, D] partial buffer: a CTA owns 32 columns, its 8 warps take
+// interleaved slabs (4 loads in flight each), then combine in a fixed order.
+__global__ void __launch_bounds__(256) perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
+                                                                      const float* __restrict__ coef, long long s_coef,
+                                                                      float* __restrict__ dDP, long long s_dDP, float accumulate) {
+  __shared__ float s_part[8][32];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int d = blockIdx.x * 32 + lane;
   const int model = blockIdx.y;
-  if (d >= D) return;
-  const float* P = partial + static_cast<long long>(model) * nslab * D;
-  float s = 0.f;
-  for (int i = 0; i < nslab; ++i) s += P[static_cast<long long>(i) * D + d];
-  const float v = s * coef[model * s_coef + d];
-  float* o = dDP + model * s_dDP + d;
-  *o = accumulate != 0.f ? *o + v : v;
+  const float* P = partial + static_cast<long long>(model) * nslab * D + d;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (d < D) {
+    int i = rg;
+    for (; i + 24 < nslab; i += 32) {
+      s0 += P[static_cast<long long>(i) * D];
+      s1 += P[static_cast<long long>(i + 8) * D];
+      s2 += P[static_cast<long long>(i + 16) * D];
+      s3 += P[static_cast<long long>(i + 24) * D];
+    }
+    for (; i < nslab; i += 8) s0 += P[static_cast<long long>(i) * D];
+  }
+  s_part[rg][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rg == 0 && d < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w][lane];
+    const float v = coef ? s * coef[model * s_coef + d] : s;
+    float* o = dDP + model * s_dDP + d;
+    *o = accumulate != 0.f ? *o + v : v;
+  }
+}
+
+// out[n] = (coef ? coef[n] : 1) * sum_r partial[r][n], fixed summation order (the column partials of the GEMM epilogues)
+int reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate, cudaStream_t s) {
+  perturb_bwd_dp_finalize_kernel<<<dim3((N + 31) / 32, 1), 256, 0, s>>>(partial, rows, N, coef, 0, out, 0, accumulate ? 1.f : 0.f);
+  PGF_CUDA_LAUNCH_CHECK("pgf_reduce_partials");
+  return PGF_OK;
 }
 
 int perturb_bwd_slabs(int B, int D, int n_models) {
@@ -452,7 +660,7 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
       perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
-  const dim3 fgrid((D + 255) / 256, n_models);
+  const dim3 fgrid((D + 31) / 32, n_models);
   perturb_bwd_dp_finalize_kernel<<<fgrid, 256, 0, s>>>(workspace, slabs, D, coef, s_coef, dDP, s_dDP, accumulate ? 1.f : 0.f);
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp(finalize)");
   return PGF_OK;

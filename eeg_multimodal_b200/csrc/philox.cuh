@@ -83,9 +83,12 @@ __device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint
 __device__ __forceinline__ float laplace_scaled_from_bits(uint32_t r, float c) {
   // (m + 0.5) * 2^-23 without an int->float conversion (I2F shares the quarter-rate pipe with MUFU):
   // 1.m as a float in [1,2), minus (1 - 2^-24); the result (2m+1)*2^-24 is exact.
-  const float v = __uint_as_float(0x3F800000u | (r & 0x7FFFFFu)) - 0.99999994039535522f;
-  const float t = lg2_ftz(v) * c;
-  return __uint_as_float(__float_as_uint(t) ^ (r & 0x80000000u));
+  uint32_t one_m;  // (r & 0x7FFFFF) | 0x3F800000 as ONE three-input logic op (both constants in registers)
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(one_m) : "r"(r), "r"(0x7FFFFFu), "r"(0x3F800000u));
+  const float v = __uint_as_float(one_m) - 0.99999994039535522f;
+  uint32_t cs;     // c with the sign bit of r XOR-ed in: c ^ (r & 0x80000000)
+  asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(cs) : "r"(__float_as_uint(c)), "r"(r), "r"(0x80000000u));
+  return lg2_ftz(v) * __uint_as_float(cs);
 }
 __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
   return laplace_scaled_from_bits(r, -0.69314718055994531f);

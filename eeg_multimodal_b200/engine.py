@@ -202,7 +202,7 @@ class HeadEngine:
             res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
                              dz=self._buf("dZ2", (M, B, H), torch.float32) if backward else None,
                              dWc=self.view("Wc", self.grad) if mode == "model" else None,
-                             dbc=self.view("bc", self.grad) if mode == "model" else None)
+                             dbc=self.view("bc", self.grad) if mode == "model" else None, want_dw=mode == "model")
             if mode == "eval":
                 return res
             dZ2 = res["dz"]
@@ -221,36 +221,46 @@ class HeadEngine:
         H1 = self._buf("H1h", (M, B, D), bf)
         H2 = self._buf("H2f", (M, B, H), torch.float32)  # tanh output kept in fp32: exact logits / loss
         W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
+        # ReLU sign bits (1 bit per activation) for the backward mask, when the width allows 128-bit mask rows
+        bits = self._buf("relu_bits", (M, B, D // 32), torch.int32) if (backward and D % 128 == 0) else None
         for i in range(M):
-            ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i])
+            ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i],
+                          aux=None if bits is None else bits[i])
             ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2[i])
         res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
                          dz=self._buf("dZ2h", (M, B, H), bf) if backward else None, dz_dtype=bf,
                          dWc=self.view("Wc", self.grad) if mode == "model" else None,
-                         dbc=self.view("bc", self.grad) if mode == "model" else None)
+                         dbc=self.view("bc", self.grad) if mode == "model" else None, want_dw=mode == "model",
+                         dz_colsum=self.view("b2", self.grad) if mode == "model" else None)   # db2 rides along
         if mode == "eval":
             return res
         dZ2 = res["dz"]
         dZ1 = self._buf("dZ1h", (M, B, D), bf)
+        gb1 = self.view("b1", self.grad)
         for i in range(M):
-            # dZ1 = (dZ2 . W2) * relu'(H1):   B operand = W2 stored [K=H, N=D]  -> MN-major
-            ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1[i])
+            # dZ1 = (dZ2 . W2) * relu'(H1):   B operand = W2 stored [K=H, N=D]  -> MN-major.  In pass 2 the bias
+            # gradient db1 = colsum(dZ1) is reduced inside the epilogue.
+            ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True,
+                          epi=L.EPI_RELUMASK_BF16 if bits is None else L.EPI_BITMASK_BF16, aux=H1[i] if bits is None else bits[i],
+                          colsum_out=gb1[i] if mode == "model" else None)
         if mode == "dp":
-            dX = self._buf("dXf", (B, D), torch.float32)   # fp32 out: feeds the dDP column reduction only
+            inj, offset = nspec
             for i in range(M):
-                ops.gemm_bf16(dZ1[i], W1h[i], dX, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32)
-                self._dDP_one(i, dX, coef, nspec, row0)
+                if inj is None:
+                    # dX = dZ1 . W1 only feeds dDP = deps * colsum(dX * noise): fused, dX never leaves TMEM
+                    ops.gemm_bf16_ddp(dZ1[i], W1h[i], M=B, N=D, K=D, b_mn=True, seed=self.seeds[i], offset=offset, row0=row0,
+                                      deps_dDP=coef[2, i], out=self.dDP[i])
+                else:   # injected-noise parity mode: materialise dX (fp32) and reduce against the supplied tensor
+                    dX = self._buf("dXf", (B, D), torch.float32)
+                    ops.gemm_bf16(dZ1[i], W1h[i], dX, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32)
+                    self._dDP_one(i, dX, coef, nspec, row0)
             return res
-        else:
-            gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
-            gb1, gb2 = self.view("b1", self.grad), self.view("b2", self.grad)
-            gW1.zero_(); gW2.zero_()
-            for i in range(M):
-                # dW = dZ^T . act: both operands are stored [K=B, *] -> MN-major, K = batch, stream-K
-                ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
-                ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
-                ops.colsum(dZ2[i], out=gb2[i])
-                ops.colsum(dZ1[i], out=gb1[i])
+        gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
+        gW1.zero_(); gW2.zero_()
+        for i in range(M):
+            # dW = dZ^T . act: both operands are stored [K=B, *] -> MN-major, K = batch, split-K
+            ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+            ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
         return res
 
     # ---- public steps ---------------------------------------------------------------------------

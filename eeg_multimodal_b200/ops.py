@@ -48,6 +48,20 @@ class Workspace:
 
 _ws = {}
 
+# optional per-launch timing (bench.py roofline): list of (tag, start_event, end_event); tag[0] names the op
+TIMING = None
+
+
+def _call(tag, name, *args):
+    """L.call, bracketed by CUDA events on the launching stream when bench.py asks for it."""
+    if TIMING is None:
+        return L.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.call(name, *args)
+    e1.record()
+    TIMING.append((tag, e0, e1))
+
 
 def workspace(tag: str) -> Workspace:
     return _ws.setdefault(tag, Workspace())
@@ -112,7 +126,7 @@ def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed
         assert gum.is_contiguous() and gum.numel() == M * 2 * B * D
     s_coef = 0 if w is None or w.dim() == 1 else w.stride(0)
     s_out = out.stride(0) if out.dim() == 3 else 0
-    L.call("pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
+    _call(("perturb_fwd", B, D, M, _dt(out), noise_mode, int(bool(want_gate))), "pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
            int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
            out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
            _stream())
@@ -132,7 +146,7 @@ def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0,
     s_dF = 0 if dF.dim() == 2 else dF.stride(0)
     s_coef = 0 if deps_dDP.dim() == 1 else deps_dDP.stride(0)
     s_out = 0 if out.dim() == 1 else out.stride(0)
-    L.call("pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(-2), s_dF, B, D, M, noise_mode, _ptr(lap), int(seed),
+    _call(("perturb_bwd_dp", B, D, M, _dt(dF)), "pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(-2), s_dF, B, D, M, noise_mode, _ptr(lap), int(seed),
            int(seed_step), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), s_coef, ws.data_ptr(), ws.numel() * 4,
            out.data_ptr(), s_out, int(accumulate), _stream())
     return out
@@ -178,7 +192,7 @@ def linear_fwd(X, W, bias, act=L.ACT_NONE, out=None):
         out = torch.empty((*X.shape[:-1], N) if nx > 1 or nm == 1 else (nm, B, N), dtype=torch.float32, device=X.device)
     sY = out.stride(0) if out.dim() == 3 else 0
     sb = 0 if bias is None or bias.dim() == 1 else bias.stride(0)
-    L.call("pgf_linear_fwd", X.data_ptr(), X.stride(-2), sX, W.data_ptr(), sW, _ptr(bias), sb, out.data_ptr(),
+    _call(("linear_fwd", B, N, K, n_models), "pgf_linear_fwd", X.data_ptr(), X.stride(-2), sX, W.data_ptr(), sW, _ptr(bias), sb, out.data_ptr(),
            out.stride(-2), sY, B, N, K, act, n_models, _stream())
     return out
 
@@ -198,7 +212,7 @@ def linear_bwd_dx(dY, W, mask_src=None, mask_mode=L.ACT_RELU, out=None):
     ws = workspace("linear_dx").get(nbytes, dY.device)
     ld_mask = 0 if mask_src is None else mask_src.stride(-2)
     s_mask = 0 if mask_src is None or mask_src.dim() == 2 else mask_src.stride(0)
-    L.call("pgf_linear_bwd_dx", dY.data_ptr(), dY.stride(-2), sdY, W.data_ptr(), sW, _ptr(mask_src), mask_mode, ld_mask, s_mask,
+    _call(("linear_bwd_dx", B, N, K, n_models), "pgf_linear_bwd_dx", dY.data_ptr(), dY.stride(-2), sdY, W.data_ptr(), sW, _ptr(mask_src), mask_mode, ld_mask, s_mask,
            out.data_ptr(), out.stride(-2), sdX, B, N, K, n_models, ws.data_ptr(), ws.numel() * 4, _stream())
     return out
 
@@ -218,37 +232,53 @@ def linear_bwd_dw(dY, X, dW=None, db=None, want_db=True, accumulate=False):
         db = torch.empty((*lead, N), dtype=torch.float32, device=dY.device)
     sdW = dW.stride(0) if dW.dim() == 3 else 0
     sdb = 0 if db is None or db.dim() == 1 else db.stride(0)
-    L.call("pgf_linear_bwd_dw", dY.data_ptr(), dY.stride(-2), sdY, X.data_ptr(), X.stride(-2), sX, dW.data_ptr(), sdW,
+    _call(("linear_bwd_dw", B, N, K, n_models), "pgf_linear_bwd_dw", dY.data_ptr(), dY.stride(-2), sdY, X.data_ptr(), X.stride(-2), sX, dW.data_ptr(), sdW,
            _ptr(db), sdb, B, N, K, int(accumulate), n_models, _stream())
     return dW, db
 
 
-# optional per-launch timing of the GEMMs (bench.py roofline): list of (tag, start_event, end_event)
-GEMM_TIMING = None
-
-
-def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, bias=None, aux=None, stream_k=False):
-    """C[M,N] = A . B^T on tcgen05 (bf16 in, fp32 accumulate in TMEM) with a fused epilogue."""
+def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16, bias=None, aux=None, stream_k=False,
+              colsum_out=None):
+    """C[M,N] = A . B^T on tcgen05 (bf16 in, fp32 accumulate in TMEM) with a fused epilogue.
+    colsum_out [N] (bf16-output epilogues): also the column sums of the fp32 epilogue values, i.e. the
+    bias gradient when C is a pre-activation gradient -- reduced per 128-row slab inside the epilogue.
+    aux: EPI_RELUMASK_BF16: bf16 [M,N] mask source; EPI_BIAS_RELU_BF16 (optional, OUT) / EPI_BITMASK_BF16 (IN):
+    int32 [M, N/32] ReLU sign bits."""
     _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _chk(C, None, "C")
-    if GEMM_TIMING is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k)
-        e1.record()
-        GEMM_TIMING.append(((M, N, K, int(a_mn), int(b_mn), epi), e0, e1))
-        return C
-    return _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k)
-
-
-def _gemm_call(A, B, C, M, N, K, a_mn, b_mn, epi, bias, aux, stream_k):
-    L.call("pgf_gemm_bf16", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), C.data_ptr(),
-           C.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux), 0 if aux is None else aux.stride(0), int(stream_k), _stream())
+    if aux is not None:
+        want = torch.bfloat16 if epi == L.EPI_RELUMASK_BF16 else torch.int32  # mask source tile | packed ReLU sign bits
+        _chk(aux, want, "aux")
+    part = None
+    if colsum_out is not None:
+        rows = L.query("pgf_gemm_partial_rows", M)
+        part = workspace("gemm_partial").get(rows * N * 4, C.device)
+    _call(("gemm", M, N, K, int(a_mn), int(b_mn), epi), "pgf_gemm_bf16", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(),
+          B.stride(0), int(b_mn), C.data_ptr(), C.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux),
+          0 if aux is None else aux.stride(0), int(stream_k), _ptr(part), _stream())
+    if colsum_out is not None:
+        _chk(colsum_out, torch.float32, "colsum_out")
+        _call(("reduce_partials", rows, N), "pgf_reduce_partials", part.data_ptr(), rows, N, None, colsum_out.data_ptr(), 0, _stream())
     return C
 
 
+def gemm_bf16_ddp(A, B, *, M, N, K, b_mn=True, seed, offset, row0, deps_dDP, out, accumulate=False):
+    """dDP = deps_dDP * colsum((A . B^T) * Laplace noise): the input-gradient GEMM of fc_layers.0 with the
+    dL/dDP reduction fused into its epilogue (the [M,N] product is never written)."""
+    _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B")
+    _chk(deps_dDP, torch.float32, "deps_dDP"); _chk(out, torch.float32, "dDP")
+    rows = L.query("pgf_gemm_partial_rows", M)
+    ws = workspace("gemm_partial").get(rows * N * 4, A.device)
+    _call(("gemm", M, N, K, 0, int(b_mn), L.EPI_DDP_PARTIAL), "pgf_gemm_bf16_ddp", A.data_ptr(), A.stride(0), B.data_ptr(),
+          B.stride(0), int(b_mn), M, N, K, int(seed), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), ws.data_ptr(),
+          ws.numel() * 4, out.data_ptr(), int(accumulate), _stream())
+    return out
+
+
 def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=True, want_logits=True, want_pred=True,
-           dz_dtype=None, dz=None, dWc=None, dbc=None):
-    """classifier + mean-CE + accuracy (+ backward).  Returns dict(logits, pred, stats, dz, dWc, dbc)."""
+           dz_dtype=None, dz=None, dWc=None, dbc=None, want_dw=True, dz_colsum=None):
+    """classifier + mean-CE + accuracy (+ backward).  Returns dict(logits, pred, stats, dz, dWc, dbc).
+    want_dw=False (pass 1 of the reference step) forms dz only; dz_colsum [H] / [M,H] receives the
+    column sums of dz (the bias gradient of fc_layers.2)."""
     _chk(h, None, "h"); _chk(Wc, torch.float32, "Wc"); _chk(bc, torch.float32, "bc")
     nh, sh = _grouped(h, 2)
     nw, sWc = _grouped(Wc, 2)
@@ -269,18 +299,18 @@ def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=
     if backward:
         if dz is None:
             dz = torch.empty(h.shape, dtype=dz_dtype or h.dtype, device=dev)
-        if dWc is None:
+        if dWc is None and want_dw:
             dWc = torch.empty((*lead, 2, H), dtype=torch.float32, device=dev)
-        if dbc is None:
+        if dbc is None and want_dw:
             dbc = torch.empty((*lead, 2), dtype=torch.float32, device=dev)
     nbytes = L.query("pgf_cls_ce_workspace", B, H, n_models)
     ws = workspace("cls_ce").get(nbytes, dev)
     g3 = lambda t: 0 if t is None or t.dim() < len(lead) + 1 or not lead else t.stride(0)
-    L.call("pgf_cls_ce", h.data_ptr(), _dt(h), h.stride(-2), sh, Wc.data_ptr(), sWc, bc.data_ptr(), sbc, _ptr(labels), slab,
+    _call(("cls_ce", B, H, n_models, _dt(h), (2 if (dWc is not None or dz_colsum is not None) else 1) if backward else 0), "pgf_cls_ce", h.data_ptr(), _dt(h), h.stride(-2), sh, Wc.data_ptr(), sWc, bc.data_ptr(), sbc, _ptr(labels), slab,
            B, H, n_models, float(loss_scale), float(grad_scale), int(bool(backward)), int(bool(through_tanh)),
            _ptr(logits), g3(logits), _ptr(pred), g3(pred), stats.data_ptr(), _ptr(dz), 0 if dz is None else _dt(dz),
            0 if dz is None else dz.stride(-2), 0 if dz is None or dz.dim() == 2 else dz.stride(0), _ptr(dWc), g3(dWc),
-           _ptr(dbc), g3(dbc), ws.data_ptr(), ws.numel() * 4, _stream())
+           _ptr(dbc), g3(dbc), _ptr(dz_colsum), g3(dz_colsum), ws.data_ptr(), ws.numel() * 4, _stream())
     return dict(logits=logits, pred=pred, stats=stats, dz=dz, dWc=dWc if backward else None, dbc=dbc if backward else None)
 
 
@@ -289,7 +319,7 @@ def adam_step(p, g, m, v, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scal
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, torch.float32, n)
         assert t.is_contiguous()
-    L.call("pgf_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(bf16_shadow), p.numel(), int(step),
+    _call(("adam", p.numel(), int(bf16_shadow is not None)), "pgf_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(bf16_shadow), p.numel(), int(step),
            float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _stream())
 
 
@@ -309,5 +339,5 @@ def colsum(x, out=None):
         out = torch.empty(N, dtype=torch.float32, device=x.device)
     nbytes = L.query("pgf_colsum_workspace", B, N)
     ws = workspace("colsum").get(nbytes, x.device)
-    L.call("pgf_colsum", x.data_ptr(), _dt(x), x.stride(0), B, N, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
+    _call(("colsum", B, N, _dt(x)), "pgf_colsum", x.data_ptr(), _dt(x), x.stride(0), B, N, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
     return out

@@ -45,6 +45,8 @@ extern "C" {
 #define PGF_EPI_STORE_F32 5
 #define PGF_EPI_BIAS_F32 6
 #define PGF_EPI_BIAS_TANH_F32 7
+#define PGF_EPI_BITMASK_BF16 9 /* C = acc * bit(aux): aux = the uint32 [M, N/32] ReLU sign bits that
+                                  PGF_EPI_BIAS_RELU_BF16 writes when its aux is non-NULL (ld_aux in words) */
 
 int pgf_version(void);
 const char* pgf_last_error(void);
@@ -125,10 +127,29 @@ int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float
  * C[M,N] = A[M,K] . B[N,K]^T, bf16 operands, fp32 accumulation in TMEM, fused epilogue `epi`.
  * a_mn / b_mn != 0: that operand is stored transposed ([K,M] / [K,N] row-major), as the
  * weight-gradient GEMMs need.  stream_k != 0 (with PGF_EPI_ATOMIC_F32, C zeroed by the caller)
- * splits K across CTAs.  bias [N] fp32; aux [M,N] bf16 (ReLU mask source).                      */
+ * splits K across CTAs.  bias [N] fp32; aux [M,N] bf16 (ReLU mask source); col_partial: below.  */
 int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C,
-                  long long ldc, int M, int N, int K, int epi, const float* bias, const void* aux,
-                  long long ld_aux, int stream_k, void* stream);
+                  long long ldc, int M, int N, int K, int epi, const float* bias, void* aux,
+                  long long ld_aux, int stream_k, float* col_partial, void* stream);
+
+/* Fused bias gradient: with a bf16-output epilogue, col_partial (optional, fp32
+ * [pgf_gemm_partial_rows(M)][N]) receives the column sums of the epilogue values of every 128-row
+ * accumulator slab; pgf_reduce_partials() sums the slabs in a fixed order:
+ *   out[n] = (coef ? coef[n] : 1) * sum_r partial[r][n]      (+= if accumulate)
+ * replaces: the `.sum(0)` of autograd's nn.Linear bias gradient (fc_layers.0.bias).              */
+int pgf_gemm_partial_rows(int M);
+int pgf_reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate,
+                        void* stream);
+
+/* ---- (a11) dL/dDP fused into the input-gradient GEMM -------------------------------------------
+ * replaces: dX = dZ1 . W1 (autograd of fc_layers.0, models.py:80) followed by the reduction of
+ *           pgf_perturb_gate_bwd_dp: dDP[n] = deps_dDP[n] * sum_m (A . B^T)[m,n] * Laplace(row0+m, n),
+ *           the noise regenerated from (seed, offset) exactly as pgf_perturb_gate_fwd drew it.
+ *           The [M,N] product only ever exists in TMEM; workspace: pgf_gemm_partial_rows(M)*N floats. */
+int pgf_gemm_bf16_ddp(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                      unsigned long long seed, unsigned int offset, unsigned long long row0,
+                      const float* deps_dDP, float* workspace, size_t workspace_bytes, float* dDP,
+                      int accumulate, void* stream);
 
 /* ---- (a9,a10,a11) classifier + softmax cross-entropy + accuracy, fwd (+bwd), grouped ---------
  * replaces: self.classifier (models.py:81) and cal_loss (base_train.py:59-65 == past_acc.py:71-77)
@@ -136,15 +157,17 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
  * h [B,H] (fp32/bf16) is the Tanh output; labels int64 [B] (slabels = 0 shares them);
  * outputs: logits [B,2], pred int64 [B] (optional); stats[model*4 + {0..3}] =
  *          {loss_sum*loss_scale, n_correct, n_correct*loss_scale, B};
- * backward!=0: dz [B,H] = (dlogits . Wc) * (1-h^2 if through_tanh), dWc [2,H], dbc [2], with
- *          dlogits = (softmax - onehot) * grad_scale.                                            */
+ * backward!=0: dz [B,H] = (dlogits . Wc) * (1-h^2 if through_tanh), with
+ *          dlogits = (softmax - onehot) * grad_scale; optional (NULL = not formed, as in pass 1 of
+ *          the reference step where zero_grad discards them, past_acc.py:206): dWc [2,H], dbc [2],
+ *          dz_colsum [H] = column sums of dz = the bias gradient of fc_layers.2.                  */
 size_t pgf_cls_ce_workspace(int B, int H, int n_models);
 int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const float* Wc, long long sWc,
                const float* bc, long long sbc, const long long* labels, long long slabels, int B, int H,
                int n_models, float loss_scale, float grad_scale, int backward, int through_tanh, float* logits,
                long long slogits, long long* pred, long long spred, float* stats, void* dz, int dz_dtype,
                long long lddz, long long sdz, float* dWc, long long sdWc, float* dbc, long long sdbc,
-               float* workspace, size_t workspace_bytes, void* stream);
+               float* dz_colsum, long long sdz_colsum, float* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (a12,f1) Adam over a flat fp32 buffer ----------------------------------------------------
  * replaces: torch.optim.Adam(...).step() for either parameter group (past_acc.py:155-160,203,212),

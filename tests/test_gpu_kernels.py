@@ -268,6 +268,17 @@ def test_cls_ce_matches_cal_loss(dev, n_models, B, H):
         assert rel_err(res["dWc"][m], wc.grad) < 5e-5 and rel_err(res["dbc"][m], b_.grad) < 5e-5
         # dz = dL/d(pre-tanh); recomputed tanh from atanh loses a little, so 1e-4 here
         assert rel_err(res["dz"][m], z.grad) < 2e-4
+    # pass-1 form (dz only: the weight-side gradients are discarded by the reference) and the fused
+    # bias gradient of fc_layers.2 (column sums of dz), fp32 and bf16 dz
+    p1 = ops.cls_ce(h.to(dev), Wc.to(dev), bc.to(dev), labels.to(dev), loss_scale=1.0 / B, grad_scale=1.0 / B, backward=True,
+                    want_dw=False)
+    assert p1["dWc"] is None and torch.equal(p1["dz"], res["dz"]) and torch.equal(p1["stats"], res["stats"])
+    for dt in (torch.float32, torch.bfloat16):
+        cs = torch.zeros(n_models, H, device=dev)
+        p2 = ops.cls_ce(h.to(dev), Wc.to(dev), bc.to(dev), labels.to(dev), loss_scale=1.0 / B, grad_scale=1.0 / B,
+                        backward=True, dz_dtype=dt, dz_colsum=cs)
+        assert rel_err(cs, res["dz"].double().sum(1)) < 5e-5
+        assert rel_err(p2["dWc"], res["dWc"]) < 1e-6 and rel_err(p2["dz"].float(), res["dz"]) < (1e-6 if dt == torch.float32 else 8e-3)
     # eval mode: no labels needed for logits/pred; bf16 activations
     ev = ops.cls_ce(h.to(dev).to(torch.bfloat16), Wc.to(dev), bc.to(dev), None, loss_scale=1.0, grad_scale=1.0, backward=False)
     ref16 = torch.einsum("mbh,mch->mbc", h.to(torch.bfloat16).double(), Wc.double()) + bc.double()[:, None]
@@ -344,8 +355,20 @@ def test_gemm_bf16_epilogues(dev):
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     for epi, ref in ((L.EPI_STORE_BF16, z), (L.EPI_BIAS_RELU_BF16, torch.relu(zb)), (L.EPI_BIAS_TANH_BF16, torch.tanh(zb)),
                      (L.EPI_RELUMASK_BF16, z * (aux.cpu().double() > 0))):
-        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias, aux=aux)
+        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias, aux=aux if epi == L.EPI_RELUMASK_BF16 else None)
         assert rel_err(out, ref) < 6e-3, (epi, rel_err(out, ref))   # bf16 output rounding: 2^-8
+    # ReLU sign bits: written by the forward epilogue (one uint32 per row x 32 columns), applied by the backward one
+    bits = torch.full((M, N // 32), -1, dtype=torch.int32, device=dev)
+    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=L.EPI_BIAS_RELU_BF16, bias=bias, aux=bits)
+    assert rel_err(out, torch.relu(zb)) < 6e-3
+    pos = (out.float() > 0).cpu()
+    got = ((bits.cpu().view(M, N // 32, 1) >> torch.arange(32, dtype=torch.int32)) & 1).bool().view(M, N)
+    assert torch.equal(got, pos)                                   # bit-exact against the stored activations
+    back = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    cs = torch.empty(N, device=dev)
+    ops.gemm_bf16(A, W, back, M=M, N=N, K=K, epi=L.EPI_BITMASK_BF16, aux=bits, colsum_out=cs)
+    ref_back = z * pos.double()
+    assert rel_err(back, ref_back) < 6e-3 and rel_err(cs, ref_back.sum(0)) < 2e-5
     o32 = torch.empty(M, N, device=dev)
     ops.gemm_bf16(A, W, o32, M=M, N=N, K=K, epi=L.EPI_BIAS_F32, bias=bias)
     assert rel_err(o32, zb) < 1e-5
@@ -373,3 +396,83 @@ def test_gemm_bf16_full_size_freivalds(dev):
     lhs = dW.double() @ v
     rhs = dZ.double().t() @ (X.double() @ v)
     assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(520, 768, 512), (128, 264, 64), (1000, 2304, 768), (4096, 2560, 768)])
+def test_gemm_fused_bias_gradient(dev, M, N, K):
+    """The ReLU-mask epilogue also reduces its fp32 values over the rows (db1 = colsum(dZ1)): per-128-row
+    slab partials inside the kernel, fixed-order sum outside -- no pass over the bf16 output."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(K, N, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)     # [K,N]: MN-major B, as dZ1 = dZ2 . W2
+    aux = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+    ref = _gemm_ref(A, W, False, True) * (aux.cpu().double() > 0)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    cs = torch.full((N,), float("nan"), device=dev)
+    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=aux, colsum_out=cs)
+    assert rel_err(out, ref) < 6e-3
+    assert rel_err(cs, ref.sum(0)) < 2e-5, rel_err(cs, ref.sum(0))
+    # deterministic: bit-identical on a second launch
+    cs2 = torch.empty(N, device=dev)
+    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=aux, colsum_out=cs2)
+    assert torch.equal(cs, cs2)
+
+
+@pytest.mark.parametrize("M,N,K,row0", [(520, 768, 512, 0), (100, 264, 64, 7), (1000, 2304, 2304, 123456), (8192, 2560, 2560, 65536 * 3)])
+def test_gemm_fused_dDP_matches_unfused(dev, M, N, K, row0):
+    """dDP from the fused input-gradient GEMM (dX stays in TMEM, noise regenerated in the epilogue) against
+    the unfused pair: fp32 dX store + pgf_perturb_gate_bwd_dp, and against the numpy Philox oracle."""
+    from eeg_multimodal_b200 import _lib as L, ops
+    from oracle import philox_ref
+
+    g = torch.Generator().manual_seed(M + K)
+    dZ = (torch.randn(M, K, generator=g) * 1e-2).to(torch.bfloat16).to(dev)
+    W = (torch.randn(K, N, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    deps = (torch.rand(N, generator=g) - 0.7).to(dev)
+    seed, offset = 980616 + M, 5
+    dX = torch.empty(M, N, device=dev)
+    ops.gemm_bf16(dZ, W, dX, M=M, N=N, K=K, b_mn=True, epi=L.EPI_STORE_F32)
+    unfused = ops.perturb_gate_bwd_dp(dX, deps, noise_mode=L.NOISE_PHILOX, seed=seed, offset=offset, row0=row0)
+    fused = torch.full((N,), float("nan"), device=dev)
+    ops.gemm_bf16_ddp(dZ, W, M=M, N=N, K=K, b_mn=True, seed=seed, offset=offset, row0=row0, deps_dDP=deps, out=fused)
+    assert rel_err(fused, unfused) < 2e-5, rel_err(fused, unfused)
+    if M <= 1000:
+        lap = torch.from_numpy(philox_ref.laplace(seed, offset, row0, M, N)).double()
+        ref = (dX.cpu().double() * lap).sum(0) * deps.cpu().double()
+        assert rel_err(fused, ref) < 2e-5, rel_err(fused, ref)
+    acc = fused.clone()
+    ops.gemm_bf16_ddp(dZ, W, M=M, N=N, K=K, b_mn=True, seed=seed, offset=offset, row0=row0, deps_dDP=deps, out=acc, accumulate=True)
+    assert rel_err(acc, 2 * fused) < 1e-6
+
+
+@pytest.mark.parametrize("dims,out_dtype", [((2048, 512), torch.bfloat16), ((768, 768, 768), torch.float32), ((2048, 512), torch.float32)])
+def test_perturb_ring_kernel_is_bit_identical_to_generic(dev, dims, out_dtype):
+    """Large batches go through the TMA-ring variant (bulk async copies into a shared-memory row ring); halves of
+    the same batch are small enough for the generic register kernel.  Same counters, same arithmetic: bit-equal."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    D = sum(dims)
+    B = 2 * ((1 << 22) // D // 2 + 37)                     # B*D >= 2^22 -> ring; B/2 * D < 2^22 -> generic
+    g = torch.Generator(device=dev).manual_seed(3)
+    blocks = [torch.randn(B, d, device=dev, generator=g) * 0.5 for d in dims]
+    for b in blocks:
+        b[5] = 0.25                                         # a constant row -> NaN row, like the reference
+    blocks[-1][7, 3] = float("nan")
+    DP = torch.randn(D, device=dev, generator=g) * 0.2
+    w, eh, _ = ops.dp_coeffs(DP, ho.exp_eps_f32(1.0))
+    full, _, mn, mx = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=123, offset=9, row0=1 << 20,
+                                           out_dtype=out_dtype, want_minmax=True)
+    h = B // 2
+    for lo in (0, h):
+        part, _, pmn, pmx = ops.perturb_gate_fwd([b[lo:lo + h] for b in blocks], w, eh, noise_mode=L.NOISE_PHILOX, seed=123,
+                                                 offset=9, row0=(1 << 20) + lo, out_dtype=out_dtype, want_minmax=True)
+        assert torch.equal(part.view(torch.int16 if out_dtype == torch.bfloat16 else torch.int32),
+                           full[lo:lo + h].view(torch.int16 if out_dtype == torch.bfloat16 else torch.int32))
+        assert torch.equal(pmn.view(torch.int32), mn[lo:lo + h].view(torch.int32))
+    assert bool(torch.isnan(full[5]).all()) and bool(torch.isnan(full[7]).all()) and bool(torch.isfinite(full[6]).all())
+    # non-private path (model.py:53-64) through the ring as well
+    nf, _, _, _ = ops.perturb_gate_fwd(blocks, None, None, noise_mode=L.NOISE_NONE, out_dtype=torch.float32)
+    np_, _, _, _ = ops.perturb_gate_fwd([b[:h] for b in blocks], None, None, noise_mode=L.NOISE_NONE, out_dtype=torch.float32)
+    assert torch.equal(nf[:h].view(torch.int32), np_.view(torch.int32))

@@ -57,6 +57,8 @@ def main():
     dW1, dW2 = torch.zeros(D, D, device=dev), torch.zeros(H, D, device=dev)
     Wc, bc = torch.randn(2, H, device=dev, generator=g) * 0.03, torch.zeros(2, device=dev)
     labels = (torch.rand(B, device=dev, generator=g) < 0.66).long()
+    bits = torch.zeros(B, D // 32, dtype=torch.int32, device=dev)
+    b1g, b2g, dDPo = torch.zeros(D, device=dev), torch.zeros(H, device=dev), torch.zeros(D, device=dev)
     P = D * D + D + H * D + H + 2 * H + 8
     p, gr, m, v = (torch.zeros(P, device=dev) for _ in range(4))
     sh = torch.zeros(P, dtype=bf, device=dev)
@@ -74,9 +76,16 @@ def main():
         ("gemm_fwd2", lambda: ops.gemm_bf16(H1, W2, H2, M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2), 0, 2 * B * H * D),
         ("gemm_dZ1", lambda: ops.gemm_bf16(dZ2, W2, dZ1, M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1), 0, 2 * B * H * D),
         ("gemm_dX", lambda: ops.gemm_bf16(dZ1, W1, Xf, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32), 0, 2 * B * D * D),
+        ("gemm_dZ1_db1", lambda: ops.gemm_bf16(dZ2, W2, dZ1, M=B, N=D, K=H, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=H1, colsum_out=b1g), 0, 2 * B * H * D),
+        ("gemm_dX_dDP_fused", lambda: ops.gemm_bf16_ddp(dZ1, W1, M=B, N=D, K=D, b_mn=True, seed=1, offset=0, row0=0, deps_dDP=deps, out=dDPo), 0, 2 * B * D * D),
+        ("gemm_fwd1_bits", lambda: ops.gemm_bf16(Xh, W1, H1, M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1, aux=bits), 0, 2 * B * D * D),
+        ("gemm_dZ1_bits", lambda: ops.gemm_bf16(dZ2, W2, dZ1, M=B, N=D, K=H, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits), 0, 2 * B * H * D),
+        ("gemm_dZ1_bits_db1", lambda: ops.gemm_bf16(dZ2, W2, dZ1, M=B, N=D, K=H, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits, colsum_out=b1g), 0, 2 * B * H * D),
         ("gemm_dW1", lambda: ops.gemm_bf16(dZ1, Xh, dW1, M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True), 0, 2 * B * D * D),
         ("gemm_dW2", lambda: ops.gemm_bf16(dZ2, H1, dW2, M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True), 0, 2 * B * H * D),
-        ("cls_ce_fwd_bwd", lambda: ops.cls_ce(H2, Wc, bc, labels, loss_scale=1 / B, grad_scale=1 / B, backward=True, dz=dZ2, dz_dtype=bf), B * H * 6, 0),
+        ("cls_ce_pass1_dz", lambda: ops.cls_ce(H2, Wc, bc, labels, loss_scale=1 / B, grad_scale=1 / B, backward=True, dz=dZ2, dz_dtype=bf, want_dw=False), B * H * 6, 0),
+        ("cls_ce_pass2_dz_dw_db2", lambda: ops.cls_ce(H2, Wc, bc, labels, loss_scale=1 / B, grad_scale=1 / B, backward=True, dz=dZ2, dz_dtype=bf, dz_colsum=b2g), B * H * 6, 0),
+        ("cls_ce_eval", lambda: ops.cls_ce(H2, Wc, bc, labels, loss_scale=1 / B, grad_scale=1 / B, backward=False), B * H * 4, 0),
         ("colsum_bf16_D", lambda: ops.colsum(dZ1), B * D * 2, 0),
         ("adam", lambda: ops.adam_step(p, gr, m, v, 1, bf16_shadow=sh), P * 30, 0),
     ]
