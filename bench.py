@@ -141,6 +141,9 @@ def kernel_work(tag):
     if kind == "colsum":
         _, b, n, dt = tag
         return f"colsum B={b} N={n}", "hbm", float(b) * n * (4 if dt == 0 else 2)
+    if kind == "linear_adam":   # read + write of W and both moments; the gradient is recomputed, never stored
+        _, b, n, k, m = tag
+        return f"linear_adam B={b} N={n} K={k} models={m}", "hbm", float(m) * n * k * 24
     if kind == "reduce_partials":
         return f"reduce_partials rows={tag[1]} N={tag[2]}", "hbm", float(tag[1]) * tag[2] * 4
     if kind in ("linear_fwd", "linear_bwd_dx", "linear_bwd_dw"):

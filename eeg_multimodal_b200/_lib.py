@@ -24,9 +24,9 @@ SIGNATURES = {
     "pgf_last_error": (C.c_char_p, []),
     "pgf_num_sms": (I, []),
     "pgf_dp_coeffs": (I, [P, P, I, I, I, P, P, P, P]),
-    "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, I, LL, LL, LL, LL, LL, U64, P]),
+    "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, I, LL, LL, LL, LL, LL, U64, P, P]),
     "pgf_perturb_gate_bwd_dp_workspace": (SZ, [I, I, I]),
-    "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, LL, I, I, I, I, P, U64, U64, U32, U64, P, LL, P, SZ, P, LL, I, P]),
+    "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, LL, I, I, I, I, P, U64, U64, P, U32, U64, P, LL, P, SZ, P, LL, I, P]),
     "pgf_minmax_norm_bwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, I, LL, I, P, LL, P, LL, P, LL, P]),
     "pgf_linear_fwd": (I, [P, LL, LL, P, LL, P, LL, P, LL, LL, I, I, I, I, I, P]),
     "pgf_linear_bwd_dx_workspace": (SZ, [I, I, I, I]),
@@ -39,6 +39,8 @@ SIGNATURES = {
     "pgf_cls_ce_workspace": (SZ, [I, I, I]),
     "pgf_cls_ce": (I, [P, I, LL, LL, P, LL, P, LL, P, LL, I, I, I, F, F, I, I, P, LL, P, LL, P, P, I, LL, LL, P, LL, P, LL, P, LL, P, SZ, P]),
     "pgf_adam_step": (I, [P, P, P, P, P, LL, I, F, F, F, F, F, P]),
+    "pgf_adam_step_strided": (I, [P, P, P, P, P, LL, LL, I, I, F, F, F, F, F, P]),
+    "pgf_linear_adam_step": (I, [P, LL, LL, P, LL, LL, I, I, I, P, P, P, P, P, P, LL, I, F, F, F, F, F, I, P]),
     "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
     "pgf_colsum_workspace": (SZ, [I, I]),
     "pgf_colsum": (I, [P, I, LL, I, I, P, P, SZ, P]),

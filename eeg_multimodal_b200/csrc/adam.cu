@@ -12,9 +12,12 @@ namespace pgf {
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
-                                                   __nv_bfloat16* __restrict__ shadow, long long n, float lr, float b1,
-                                                   float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
-  const float step_size = lr / bc1;
+                                                   __nv_bfloat16* __restrict__ shadow, long long n, const AdamCoef c,
+                                                   long long model_stride) {
+  // blockIdx.y walks the models of a strided group (segment [0,n) of every model's flat buffer)
+  const long long base = static_cast<long long>(blockIdx.y) * model_stride;
+  p += base; g += base; m += base; v += base;
+  if (shadow) shadow += base;
   const long long n4 = n >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -25,13 +28,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     float pe[4] = {P.x, P.y, P.z, P.w}, ge[4] = {G.x, G.y, G.z, G.w}, me[4] = {M.x, M.y, M.z, M.w},
           ve[4] = {V.x, V.y, V.z, V.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float gg = ge[e] * grad_scale;
-      me[e] = me[e] + (gg - me[e]) * (1.f - b1);
-      ve[e] = ve[e] * b2 + (1.f - b2) * gg * gg;
-      const float denom = sqrtf(ve[e]) / bc2_sqrt + eps;
-      pe[e] = pe[e] - step_size * (me[e] / denom);
-    }
+    for (int e = 0; e < 4; ++e) adam_update(pe[e], me[e], ve[e], ge[e], c);
     reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
@@ -45,33 +42,38 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   // tail (n % 4 elements), handled by the first threads of block 0
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
-    const float gg = g[i] * grad_scale;
-    const float mm = m[i] + (gg - m[i]) * (1.f - b1);
-    const float vv = v[i] * b2 + (1.f - b2) * gg * gg;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    const float pp = p[i] - step_size * (mm / denom);
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_update(pp, mm, vv, g[i], c);
     p[i] = pp; m[i] = mm; v[i] = vv;
     if (shadow) shadow[i] = __float2bfloat16_rn(pp);
   }
 }
 
+AdamCoef make_adam_coef(int step, float lr, float b1, float b2, float eps, float grad_scale) {
+  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+  AdamCoef c;
+  c.b1 = b1; c.b2 = b2; c.eps = eps; c.grad_scale = grad_scale;
+  c.step_size = lr / static_cast<float>(bc1);
+  c.bc2_sqrt = static_cast<float>(sqrt(bc2));
+  return c;
+}
+
 int adam_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, int step, float lr, float b1,
-              float b2, float eps, float grad_scale, cudaStream_t s) {
-  if (n <= 0) return PGF_OK;
+              float b2, float eps, float grad_scale, cudaStream_t s, long long model_stride, int n_models) {
+  if (n <= 0 || n_models <= 0) return PGF_OK;
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15) {
     set_error("pgf_adam_step: buffers must be 16-byte aligned");
     return PGF_ERR_ARG;
   }
-  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
   long long blocks = (n / 4 + 255) / 256;
-  const long long cap = 8LL * num_sms();
+  const long long cap = (8LL * num_sms() + n_models - 1) / n_models;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p, g, m, v, static_cast<__nv_bfloat16*>(shadow), n, lr, b1, b2, eps,
-                                                            static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-                                                            grad_scale);
+  adam_kernel<<<dim3(static_cast<unsigned>(blocks), n_models), 256, 0, s>>>(p, g, m, v, static_cast<__nv_bfloat16*>(shadow), n,
+                                                                            make_adam_coef(step, lr, b1, b2, eps, grad_scale),
+                                                                            model_stride);
   PGF_CUDA_LAUNCH_CHECK("pgf_adam_step");
   return PGF_OK;
 }

@@ -54,7 +54,7 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
                          unsigned long long row0, float tau, int hard, int want_gate, void* out, int out_dtype,
                          long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, int n_models,
                          long long sx0, long long sx1, long long sx2, long long s_coef, long long s_out,
-                         unsigned long long seed_step, void* stream) {
+                         unsigned long long seed_step, const unsigned long long* model_seeds, void* stream) {
   if (B == 0 || n_models == 0) return PGF_OK;  // empty batch: nothing to do
   PGF_CHECK_ARG(n_models > 0 && (sx0 % 4) == 0 && (sx1 % 4) == 0 && (sx2 % 4) == 0 && (s_coef % 4) == 0 && (s_out % 4) == 0,
                 "pgf_perturb_gate_fwd: n_models < 0 or model strides not multiples of 4");
@@ -80,7 +80,7 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   a.d[0] = d0; a.d[1] = d1; a.d[2] = d2;
   a.D = d0 + d1 + d2;
   a.B = B;
-  a.n_models = n_models; a.s_coef = s_coef; a.s_out = s_out; a.seed_step = seed_step;
+  a.n_models = n_models; a.s_coef = s_coef; a.s_out = s_out; a.seed_step = seed_step; a.model_seeds = model_seeds;
   memset(&a.rk, 0, sizeof(a.rk));
   a.w = w; a.eps_hat = eps_hat; a.lap = lap; a.gum = gum;
   a.seed = seed; a.offset = offset; a.row0 = row0;
@@ -96,7 +96,8 @@ size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D, int n_models) {
 
 int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, long long s_dF, int B, int D, int n_models,
                             int noise_mode, const float* lap, unsigned long long seed, unsigned long long seed_step,
-                            unsigned int offset, unsigned long long row0, const float* deps_dDP, long long s_coef,
+                            const unsigned long long* model_seeds, unsigned int offset, unsigned long long row0,
+                            const float* deps_dDP, long long s_coef,
                             float* workspace, size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate,
                             void* stream) {
   PGF_CHECK_ARG(D > 0 && (D % 4) == 0 && dDP && deps_dDP && n_models >= 0, "pgf_perturb_gate_bwd_dp: bad D / NULL outputs");
@@ -111,8 +112,8 @@ int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, long lon
   PGF_CHECK_ARG(noise_mode == PGF_NOISE_INJECTED || noise_mode == PGF_NOISE_PHILOX, "pgf_perturb_gate_bwd_dp: bad noise_mode");
   if (noise_mode == PGF_NOISE_INJECTED) PGF_CHECK_ARG(lap, "pgf_perturb_gate_bwd_dp: injected mode needs lap");
   PGF_CHECK_ARG(workspace, "pgf_perturb_gate_bwd_dp: workspace is NULL");
-  return perturb_gate_bwd_dp(dF, dF_dtype, ld, s_dF, B, D, n_models, noise_mode, lap, seed, seed_step, offset, row0, deps_dDP,
-                             s_coef, workspace, workspace_bytes, dDP, s_dDP, accumulate, static_cast<cudaStream_t>(stream));
+  return perturb_gate_bwd_dp(dF, dF_dtype, ld, s_dF, B, D, n_models, noise_mode, lap, seed, seed_step, model_seeds, offset, row0,
+                             deps_dDP, s_coef, workspace, workspace_bytes, dDP, s_dDP, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 int pgf_minmax_norm_bwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
@@ -257,6 +258,34 @@ int pgf_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shado
   if (n == 0) return PGF_OK;
   PGF_CHECK_ARG(p && g && m && v, "pgf_adam_step: NULL argument");
   return adam_step(p, g, m, v, bf16_shadow, n, step, lr, beta1, beta2, eps, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_adam_step_strided(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, long long model_stride,
+                          int n_models, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                          void* stream) {
+  PGF_CHECK_ARG(n >= 0 && step >= 1 && n_models >= 0, "pgf_adam_step_strided: bad n / step / n_models");
+  if (n == 0 || n_models == 0) return PGF_OK;
+  PGF_CHECK_ARG(p && g && m && v && (model_stride % 4) == 0 && ((n % 4) == 0 || n_models == 1),
+                "pgf_adam_step_strided: NULL argument, or segment length / stride not a multiple of 4");
+  return adam_step(p, g, m, v, bf16_shadow, n, step, lr, beta1, beta2, eps, grad_scale, static_cast<cudaStream_t>(stream),
+                   model_stride, n_models);
+}
+
+int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX, int B,
+                         int N, int K, float* W, float* mW, float* vW, float* bias, float* mb, float* vb, long long sP,
+                         int step, float lr, float beta1, float beta2, float eps, float grad_scale, int n_models,
+                         void* stream) {
+  if (n_models == 0 || N == 0 || K == 0) return PGF_OK;
+  PGF_CHECK_ARG(dY && X && W && mW && vW && B > 0 && N > 0 && K > 0 && step >= 1, "pgf_linear_adam_step: bad argument");
+  PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && (sX % 4) == 0 && (sP % 4) == 0 && aligned16(X) && aligned16(W) &&
+                    aligned16(mW) && aligned16(vW),
+                "pgf_linear_adam_step: K, ldx, strides must be multiples of 4 and X, W, mW, vW 16-byte aligned");
+  PGF_CHECK_ARG(!bias || (mb && vb), "pgf_linear_adam_step: bias needs its moment buffers");
+  LinAdamArgs a;
+  a.dY = dY; a.ldy = ldy; a.sdY = sdY; a.X = X; a.ldx = ldx; a.sX = sX; a.W = W; a.mW = mW; a.vW = vW;
+  a.bias = bias; a.mb = mb; a.vb = vb; a.sP = sP; a.B = B; a.N = N; a.K = K; a.rows_per_cta = 0;
+  a.c = make_adam_coef(step, lr, beta1, beta2, eps, grad_scale);
+  return linear_adam_step(a, n_models, static_cast<cudaStream_t>(stream));
 }
 
 int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {

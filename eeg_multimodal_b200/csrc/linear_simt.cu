@@ -11,6 +11,8 @@
 //   dx  : dX[b,k] = sum_n dY[b,n] W[n,k]  (* relu mask)        read W once
 //   dw  : dW[n,k] = sum_b dY[b,n] X[b,k],  db[n] = sum_b dY    write dW once
 // Accumulation is fp32 FMA in a fixed order (deterministic; no atomics).
+#include <stdlib.h>
+
 #include "pgf_kernels.cuh"
 
 namespace pgf {
@@ -345,6 +347,118 @@ int linear_bwd_dw(const LinDwArgs& a_in, int n_models, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(rows) * TB * sizeof(float);
   linear_dw_kernel<<<grid, 128, smem, s>>>(a);
   PGF_CUDA_LAUNCH_CHECK("pgf_linear_bwd_dw");
+  return PGF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dW fused into Adam (small batch): dW[n,k] = sum_b dY[b,n] X[b,k] is a rank-B outer product, so at the
+// reference batch size it is recomputed inside the optimiser (8 FMAs per element) instead of being written
+// to HBM by one kernel and read back by the next: 24 instead of 32 bytes per parameter and step.
+// Same thread <-> element mapping as linear_dw_kernel; the arithmetic per element is adam_update().
+// ------------------------------------------------------------------------------------------
+template <int U>  // rows in flight per thread (3 x 128-bit loads each)
+__global__ void __launch_bounds__(128) linear_adam_kernel(const LinAdamArgs a) {
+  extern __shared__ float sdy[];  // [rows_per_cta][TB]
+  const int model = blockIdx.z;
+  const int n0 = blockIdx.y * a.rows_per_cta, n1 = min(a.N, n0 + a.rows_per_cta);
+  const int k4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K4 = a.K >> 2;
+  const float* dY = a.dY + model * a.sdY;
+  for (int i = threadIdx.x; i < (n1 - n0) * TB; i += blockDim.x) {
+    const int n = i / TB, b = i - n * TB;
+    sdy[i] = b < a.B ? dY[b * a.ldy + n0 + n] : 0.f;
+  }
+  __syncthreads();
+  if (a.bias && blockIdx.x == 0) {  // bias: gradient = column sum of dY
+    for (int n = threadIdx.x; n < n1 - n0; n += blockDim.x) {
+      float g = 0.f;
+#pragma unroll
+      for (int b = 0; b < TB; ++b) g += sdy[n * TB + b];
+      const long long i = model * a.sP + n0 + n;
+      float p = a.bias[i], m = a.mb[i], v = a.vb[i];
+      adam_update(p, m, v, g, a.c);
+      a.bias[i] = p; a.mb[i] = m; a.vb[i] = v;
+    }
+  }
+  if (k4 >= K4) return;
+  float4 x[TB];
+  const float* X = a.X + model * a.sX + 4 * k4;
+#pragma unroll
+  for (int b = 0; b < TB; ++b) x[b] = b < a.B ? *reinterpret_cast<const float4*>(X + b * a.ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4* W = reinterpret_cast<float4*>(a.W + model * a.sP) + k4;
+  float4* M = reinterpret_cast<float4*>(a.mW + model * a.sP) + k4;
+  float4* V = reinterpret_cast<float4*>(a.vW + model * a.sP) + k4;
+  int n = n0;
+  for (; n + U <= n1; n += U) {
+    float4 p[U], m[U], v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long o = static_cast<long long>(n + u) * K4;
+      p[u] = W[o]; m[u] = M[o]; v[u] = V[o];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 g0 = *reinterpret_cast<const float4*>(sdy + (n - n0 + u) * TB);
+      const float4 g1 = *reinterpret_cast<const float4*>(sdy + (n - n0 + u) * TB + 4);
+      const float g[TB] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < TB; ++b) {   // same order as linear_dw_kernel: bit-identical gradient
+        o.x = fmaf(g[b], x[b].x, o.x);
+        o.y = fmaf(g[b], x[b].y, o.y);
+        o.z = fmaf(g[b], x[b].z, o.z);
+        o.w = fmaf(g[b], x[b].w, o.w);
+      }
+      adam_update(p[u].x, m[u].x, v[u].x, o.x, a.c);
+      adam_update(p[u].y, m[u].y, v[u].y, o.y, a.c);
+      adam_update(p[u].z, m[u].z, v[u].z, o.z, a.c);
+      adam_update(p[u].w, m[u].w, v[u].w, o.w, a.c);
+      const long long off = static_cast<long long>(n + u) * K4;
+      W[off] = p[u]; M[off] = m[u]; V[off] = v[u];
+    }
+  }
+  for (; n < n1; ++n) {
+    const long long off = static_cast<long long>(n) * K4;
+    float4 p = W[off], m = M[off], v = V[off];
+    const float4 g0 = *reinterpret_cast<const float4*>(sdy + (n - n0) * TB);
+    const float4 g1 = *reinterpret_cast<const float4*>(sdy + (n - n0) * TB + 4);
+    const float g[TB] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < TB; ++b) {
+      o.x = fmaf(g[b], x[b].x, o.x);
+      o.y = fmaf(g[b], x[b].y, o.y);
+      o.z = fmaf(g[b], x[b].z, o.z);
+      o.w = fmaf(g[b], x[b].w, o.w);
+    }
+    adam_update(p.x, m.x, v.x, o.x, a.c);
+    adam_update(p.y, m.y, v.y, o.y, a.c);
+    adam_update(p.z, m.z, v.z, o.z, a.c);
+    adam_update(p.w, m.w, v.w, o.w, a.c);
+    W[off] = p; M[off] = m; V[off] = v;
+  }
+}
+
+int linear_adam_step(const LinAdamArgs& a_in, int n_models, cudaStream_t s) {
+  LinAdamArgs a = a_in;
+  if (a.B > TB) {
+    set_error("pgf_linear_adam_step: the fused gradient+Adam kernel handles batches up to %d rows (got %d)", TB, a.B);
+    return PGF_ERR_UNSUPPORTED;
+  }
+  const int kctas = (a.K / 4 + 127) / 128;
+  long long want = (8LL * num_sms() + static_cast<long long>(kctas) * n_models - 1) / (static_cast<long long>(kctas) * n_models);
+  if (want < 1) want = 1;
+  int rows = static_cast<int>((a.N + want - 1) / want);
+  static const int rows_min = getenv("PGF_LINADAM_ROWS_MIN") ? atoi(getenv("PGF_LINADAM_ROWS_MIN")) : 16;
+  static const int unroll = getenv("PGF_LINADAM_U") ? atoi(getenv("PGF_LINADAM_U")) : 2;
+  if (rows < rows_min) rows = rows_min;
+  if (rows > 1024) rows = 1024;
+  a.rows_per_cta = rows;
+  const dim3 grid(kctas, (a.N + rows - 1) / rows, n_models);
+  const size_t smem = static_cast<size_t>(rows) * TB * sizeof(float);
+  if (unroll >= 4) linear_adam_kernel<4><<<grid, 128, smem, s>>>(a);
+  else linear_adam_kernel<2><<<grid, 128, smem, s>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_linear_adam_step");
   return PGF_OK;
 }
 

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
   const float* x0 = a.x[0] + model * a.sx[0];
   const float* x1 = a.d[1] ? a.x[1] + model * a.sx[1] : nullptr;
   const float* x2 = a.d[2] ? a.x[2] + model * a.sx[2] : nullptr;
-  const unsigned long long seed = a.seed + static_cast<unsigned long long>(model) * a.seed_step;
+  const unsigned long long seed = a.model_seeds ? a.model_seeds[model] : a.seed + static_cast<unsigned long long>(model) * a.seed_step;
   const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
   const long long BD = static_cast<long long>(a.B) * a.D;
   const float* lap = a.lap ? a.lap + model * BD : nullptr;
@@ -450,7 +450,7 @@ int perturb_gate_fwd(const PerturbFwdArgs& a_in, int noise, int out_dtype, bool 
   a.rk = philox_make_keys(a.seed);
   // Large batches: one launch per model, so the Philox round keys are compile-time-indexed kernel
   // arguments (constant-bank operands).  Small batches (the B=8 sweep): one grouped launch.
-  const bool split = noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate &&
+  const bool split = noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate && !a.model_seeds &&
                      static_cast<long long>(a.B) * a.D >= (1LL << 22);
   if (!split) return perturb_gate_fwd_one(a, noise, out_dtype, want_gate, s);
   const size_t esz = out_dtype == PGF_DT_F32 ? 4 : 2;
@@ -487,6 +487,7 @@ struct PerturbBwdArgs {
   const float* lap;
   unsigned long long seed;
   unsigned long long seed_step;
+  const unsigned long long* model_seeds;
   int nslab;
   PhiloxKeys rk;
   unsigned int offset;
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
   const int slab = blockIdx.y, model = blockIdx.z;
   const int r0 = slab * a.rows_per_slab;
   const int r1 = min(a.B, r0 + a.rows_per_slab);
-  const unsigned long long seed = a.seed + static_cast<unsigned long long>(model) * a.seed_step;
+  const unsigned long long seed = a.model_seeds ? a.model_seeds[model] : a.seed + static_cast<unsigned long long>(model) * a.seed_step;
   const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
   const void* dFm = static_cast<const char*>(a.dF) + model * a.s_dF * static_cast<long long>(sizeof(InT));
   const float* lapm = a.lap ? a.lap + static_cast<long long>(model) * a.B * a.D : nullptr;
@@ -618,9 +619,10 @@ int perturb_bwd_slabs(int B, int D, int n_models) {
 }
 
 int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF, int B, int D, int n_models, int noise,
-                        const float* lap, unsigned long long seed, unsigned long long seed_step, unsigned int offset,
-                        unsigned long long row0, const float* coef, long long s_coef, float* workspace,
-                        size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate, cudaStream_t s) {
+                        const float* lap, unsigned long long seed, unsigned long long seed_step,
+                        const unsigned long long* model_seeds, unsigned int offset, unsigned long long row0, const float* coef,
+                        long long s_coef, float* workspace, size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate,
+                        cudaStream_t s) {
   const int slabs = perturb_bwd_slabs(B, D, n_models);
   const size_t need = static_cast<size_t>(n_models) * slabs * D * sizeof(float);
   if (workspace_bytes < need) {
@@ -636,6 +638,7 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
   a.lap = lap;
   a.seed = seed;
   a.seed_step = seed_step;
+  a.model_seeds = model_seeds;
   a.nslab = slabs;
   a.offset = offset;
   a.row0 = row0;
@@ -648,7 +651,7 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
       perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float, false><<<grid, 128, 0, s>>>(a);
     else
       perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
-  } else if (n_models == 1) {
+  } else if (n_models == 1 && !model_seeds) {
     if (dtype == PGF_DT_F32)
       perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, true><<<grid, 128, 0, s>>>(a);
     else

@@ -75,10 +75,13 @@ class HeadEngine:
         self.shadow = torch.zeros(self.M, self.P, device=dev, dtype=torch.bfloat16) if precision == "bf16" else None
         self.t_model = 0
         self.t_dp = 0
+        self.fuse_adam = True   # fp32 small-batch path: weight gradients recomputed inside the Adam kernel
         self.noise_offset = 0
         self._bufs = {}
         self._injected = None
         self.exp_eps_dev = torch.tensor(self.exp_eps, dtype=torch.float32, device=dev)
+        # arbitrary per-model seeds: a device array read by the grouped kernels (one launch for the whole sweep)
+        self.seeds_dev = torch.tensor([s if s < 2 ** 63 else s - 2 ** 64 for s in self.seeds], dtype=torch.int64, device=dev)
         self._init_params(init_seed, dp_init)
 
     # ---- parameters ----------------------------------------------------------------------------
@@ -156,7 +159,10 @@ class HeadEngine:
         elif self.seed_step is not None:   # one grouped launch for the whole ensemble
             ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, seed=self.seeds[0],
                                  seed_step=self.seed_step, offset=offset, row0=row0, tau=self.tau, hard=hard, out=out, n_models=M)
-        else:
+        elif blocks[0].shape[-2] * self.D < (1 << 22):   # small batches: one grouped launch, seeds from the device array
+            ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, model_seeds=self.seeds_dev, offset=offset,
+                                 row0=row0, tau=self.tau, hard=hard, out=out, n_models=M)
+        else:                                            # large batches: per-model launches of the TMA-ring kernel
             for i in range(M):
                 bl = [b[i] if b.dim() == 3 else b for b in blocks]
                 ops.perturb_gate_fwd(bl, coef[0, i], coef[1, i], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
@@ -179,16 +185,19 @@ class HeadEngine:
             ops.perturb_gate_bwd_dp(dX, coef[2], noise_mode=L.NOISE_PHILOX, seed=self.seeds[0], seed_step=self.seed_step,
                                     offset=offset, row0=row0, out=self.dDP)
         else:
-            for i in range(self.M):
-                self._dDP_one(i, dX[i], coef, noise_spec, row0)
+            ops.perturb_gate_bwd_dp(dX, coef[2], noise_mode=L.NOISE_PHILOX, model_seeds=self.seeds_dev, offset=offset, row0=row0,
+                                    out=self.dDP)
 
     def _labels(self, labels):
         labels = labels.reshape(labels.shape[0], -1)[:, 0] if labels.dim() == 2 and labels.shape[-1] == 1 else labels
         return labels.contiguous()
 
     # ---- one forward(+backward) pass -----------------------------------------------------------
-    def _pass(self, blocks, labels, hard, mode, row0=0, global_batch=None):
-        """mode: 'dp' (pass 1), 'model' (pass 2) or 'eval'.  Returns the cls_ce result dict."""
+    def _pass(self, blocks, labels, hard, mode, row0=0, global_batch=None, fuse_adam=False):
+        """mode: 'dp' (pass 1), 'model' (pass 2) or 'eval'.  Returns the cls_ce result dict.
+        fuse_adam (fp32 path, batch <= 8, no gradient all-reduce): the Adam step of pass 2 is applied inside the
+        pass, with the weight gradients recomputed in the optimiser kernel instead of written to HBM;
+        res['adam_done'] tells the caller."""
         B = blocks[0].shape[-2]
         M, D, H = self.M, self.D, self.H
         gb = float(global_batch or B)
@@ -210,6 +219,14 @@ class HeadEngine:
             if mode == "dp":
                 dX = ops.linear_bwd_dx(dZ1, W1, out=self._buf("dX", (M, B, D), torch.float32))
                 self._dDP(dX, coef, nspec, row0)
+            elif fuse_adam and B <= 8:
+                kw = dict(step=self.t_model, lr=self.lr, betas=self.betas, eps=self.adam_eps)
+                for wn, bn, dY, inp in (("W2", "b2", dZ2, H1), ("W1", "b1", dZ1, X)):
+                    ops.linear_adam_step(dY, inp, self.view(wn), self.view(wn, self.m), self.view(wn, self.v),
+                                         self.view(bn), self.view(bn, self.m), self.view(bn, self.v), **kw)
+                off = self.layout["Wc"][0]   # [Wc | bc] of every model: gradients came from cls_ce
+                ops.adam_step_strided(self.flat[:, off:], self.grad[:, off:], self.m[:, off:], self.v[:, off:], **kw)
+                res["adam_done"] = True
             else:
                 ops.linear_bwd_dw(dZ2, H1, dW=self.view("W2", self.grad), db=self.view("b2", self.grad))
                 ops.linear_bwd_dw(dZ1, X, dW=self.view("W1", self.grad), db=self.view("b1", self.grad))
@@ -277,12 +294,14 @@ class HeadEngine:
                 grad_hook(self.dDP)
             self.t_dp += 1
             ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
-        res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch)
-        if grad_hook is not None:
-            grad_hook(self.grad)
         self.t_model += 1
-        ops.adam_step(self.flat, self.grad, self.m, self.v, self.t_model, self.lr, self.betas, self.adam_eps,
-                      bf16_shadow=self.shadow)
+        res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch,
+                         fuse_adam=grad_hook is None and self.fuse_adam)
+        if not res.get("adam_done"):
+            if grad_hook is not None:
+                grad_hook(self.grad)
+            ops.adam_step(self.flat, self.grad, self.m, self.v, self.t_model, self.lr, self.betas, self.adam_eps,
+                          bf16_shadow=self.shadow)
         st = res["stats"].view(self.M, 4)
         return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1])
 

@@ -78,6 +78,15 @@ def _exp_eps_tensor(exp_eps, n_models, device):
     return t.contiguous()
 
 
+def _seeds_ptr(model_seeds, n_models):
+    """Device int64 tensor [n_models] of per-model Philox seeds (bit pattern of the uint64 the kernels read)."""
+    if model_seeds is None:
+        return None
+    _chk(model_seeds, torch.int64, "model_seeds")
+    assert model_seeds.is_contiguous() and model_seeds.numel() == n_models
+    return model_seeds.data_ptr()
+
+
 def dp_coeffs(DP: torch.Tensor, exp_eps, fixed: bool = True, out=None):
     """(w, eps_hat, deps_dDP), each shaped like DP ([D] or [n_models, D]).  models.py:73,75.
     `exp_eps`: float (one model), list, or device tensor [n_models] of e^eps values."""
@@ -95,7 +104,7 @@ def dp_coeffs(DP: torch.Tensor, exp_eps, fixed: bool = True, out=None):
 
 def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed=0, offset=0, row0=0, tau=1.0,
                      hard=True, want_gate=False, out_dtype=torch.float32, out=None, want_gate_idx=False,
-                     want_minmax=False, n_models=1, seed_step=0):
+                     want_minmax=False, n_models=1, seed_step=0, model_seeds=None):
     """models.py:69-79 in one kernel.  Returns (out, gate_idx|None, row_min|None, row_max|None).
     Single model: blocks [B,Di], out [B,D].  Grouped (n_models > 1): blocks [B,Di] (shared batch) or
     [M,B,Di]; w/eps_hat [M,D]; out [M,B,D]; lap [M,B,D]; gum [M,2,B,D]; model m uses seed + m*seed_step."""
@@ -129,12 +138,12 @@ def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed
     _call(("perturb_fwd", B, D, M, _dt(out), noise_mode, int(bool(want_gate))), "pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
            int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
            out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
-           _stream())
+           _seeds_ptr(model_seeds, M), _stream())
     return out, gate_idx, rmin, rmax
 
 
 def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0, row0=0, out=None, accumulate=False,
-                        seed_step=0):
+                        seed_step=0, model_seeds=None):
     """dDP = deps_dDP * sum_b dF * noise.  Autograd of models.py:75-76.  dF [B,D] or [M,B,D]."""
     _chk(dF, None, "dF")
     B, D = dF.shape[-2:]
@@ -147,7 +156,8 @@ def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0,
     s_coef = 0 if deps_dDP.dim() == 1 else deps_dDP.stride(0)
     s_out = 0 if out.dim() == 1 else out.stride(0)
     _call(("perturb_bwd_dp", B, D, M, _dt(dF)), "pgf_perturb_gate_bwd_dp", dF.data_ptr(), _dt(dF), dF.stride(-2), s_dF, B, D, M, noise_mode, _ptr(lap), int(seed),
-           int(seed_step), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), s_coef, ws.data_ptr(), ws.numel() * 4,
+           int(seed_step), _seeds_ptr(model_seeds, M), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), s_coef,
+           ws.data_ptr(), ws.numel() * 4,
            out.data_ptr(), s_out, int(accumulate), _stream())
     return out
 
@@ -321,6 +331,37 @@ def adam_step(p, g, m, v, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scal
         assert t.is_contiguous()
     _call(("adam", p.numel(), int(bf16_shadow is not None)), "pgf_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(bf16_shadow), p.numel(), int(step),
            float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _stream())
+
+
+def adam_step_strided(p, g, m, v, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """Adam over a [n_models, n] strided view (row stride = model stride) of the flat buffers: one launch."""
+    for t in (p, g, m, v):
+        _chk(t, torch.float32, "adam buffer")
+        assert t.dim() == 2 and t.shape == p.shape and t.stride() == p.stride()
+    _call(("adam", p.numel(), 0), "pgf_adam_step_strided", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), None, p.shape[1],
+          p.stride(0), p.shape[0], int(step), float(lr), float(betas[0]), float(betas[1]), float(eps), float(grad_scale), _stream())
+
+
+def linear_adam_step(dY, X, W, mW, vW, bias, mb, vb, step, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """Adam step of one nn.Linear with the weight gradient dY^T X (and bias gradient colsum(dY)) recomputed in
+    the optimiser kernel instead of materialised (batch <= 8).  Grouped: dY [M,B,N], X [M,B,K], W/mW/vW [M,N,K]
+    views of per-model flat buffers with a common model stride; bias/mb/vb [M,N] views of the same buffers."""
+    for t, n in ((dY, "dY"), (X, "X"), (W, "W"), (mW, "mW"), (vW, "vW")):
+        _chk(t, torch.float32, n)
+    nm, sP = _grouped(W, 2)
+    B, N = dY.shape[-2:]
+    K = X.shape[-1]
+    assert W.shape[-2:] == (N, K) and W.stride(-2) == K, "W must be dense [N,K]"
+    for t in (mW, vW):
+        assert t.shape == W.shape and t.stride() == W.stride()
+    if bias is not None:
+        for t in (bias, mb, vb):
+            _chk(t, torch.float32, "bias")
+            assert (0 if t.dim() == 1 else t.stride(0)) == sP
+    _call(("linear_adam", B, N, K, nm), "pgf_linear_adam_step", dY.data_ptr(), dY.stride(-2), 0 if dY.dim() == 2 else dY.stride(0),
+          X.data_ptr(), X.stride(-2), 0 if X.dim() == 2 else X.stride(0), B, N, K, W.data_ptr(), mW.data_ptr(), vW.data_ptr(),
+          _ptr(bias), _ptr(mb), _ptr(vb), sP, int(step), float(lr), float(betas[0]), float(betas[1]), float(eps),
+          float(grad_scale), nm, _stream())
 
 
 def cast_bf16(src, dst=None):

@@ -76,14 +76,16 @@ int pgf_dp_coeffs(const float* DP, const float* exp_eps, int fixed_formula, int 
  * out: [B,D] fp32 or bf16 (ld_out); gate_idx [B,D] uint8, row_min/row_max [B]: optional.
  * grouped: n_models launches' worth in one grid; sx* / s_coef / s_out are the model strides of the
  *          blocks (0 = one batch shared by the whole sweep), of w/eps_hat and of out; lap, gum,
- *          gate_idx, row_min/max are contiguous per model; model m uses seed + m*seed_step.     */
+ *          gate_idx, row_min/max are contiguous per model; model m uses seed + m*seed_step, or
+ *          model_seeds[m] when that DEVICE array [n_models] is given (arbitrary eps x seed grids).   */
 int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1,
                          const float* x2, int d2, long long ld2, const float* w, const float* eps_hat, int B,
                          int noise_mode, const float* lap, const float* gum, unsigned long long seed,
                          unsigned int offset, unsigned long long row0, float tau, int hard, int want_gate,
                          void* out, int out_dtype, long long ld_out, unsigned char* gate_idx, float* row_min,
                          float* row_max, int n_models, long long sx0, long long sx1, long long sx2,
-                         long long s_coef, long long s_out, unsigned long long seed_step, void* stream);
+                         long long s_coef, long long s_out, unsigned long long seed_step,
+                         const unsigned long long* model_seeds, void* stream);
 
 /* ---- (a11) dL/dDP through the perturbation ----------------------------------------------------
  * replaces: autograd through models.py:75-76: dDP[d] = deps_dDP[d] * sum_b dF[b,d] * noise[b,d]
@@ -92,7 +94,8 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
 size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D, int n_models);
 int pgf_perturb_gate_bwd_dp(const void* dF, int dF_dtype, long long ld, long long s_dF, int B, int D, int n_models,
                             int noise_mode, const float* lap, unsigned long long seed,
-                            unsigned long long seed_step, unsigned int offset, unsigned long long row0,
+                            unsigned long long seed_step, const unsigned long long* model_seeds,
+                            unsigned int offset, unsigned long long row0,
                             const float* deps_dDP, long long s_coef, float* workspace, size_t workspace_bytes,
                             float* dDP, long long s_dDP, int accumulate, void* stream);
 
@@ -175,6 +178,24 @@ int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const fl
  *           bf16 copy of the updated parameters for the tensor-core path.                        */
 int pgf_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* The same update over the segment [0,n) of each of n_models flat buffers `model_stride` elements apart
+ * (one launch for, e.g., the classifier parameters of a whole sweep).                             */
+int pgf_adam_step_strided(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
+                          long long model_stride, int n_models, int step, float lr, float beta1, float beta2,
+                          float eps, float grad_scale, void* stream);
+
+/* ---- (a11,a12,f1) weight gradient fused into Adam, small batch (B <= 8), grouped -----------------
+ * replaces: autograd's dW = dY^T X, db = colsum(dY) of one nn.Linear (models.py:46-51) followed by
+ *           model_optimizer.step() on that layer (past_acc.py:212).  At the reference batch size the
+ *           gradient is a rank-8 outer product: it is recomputed per element inside the optimiser, so
+ *           dW is never written to / read from HBM (24 instead of 32 bytes per parameter and step).
+ * W, mW, vW: [N,K] weight and Adam moments; bias, mb, vb: [N] (optional); all six live in per-model
+ * flat buffers with the common model stride sP.  Same update arithmetic as pgf_adam_step.         */
+int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const float* X, long long ldx,
+                         long long sX, int B, int N, int K, float* W, float* mW, float* vW, float* bias,
+                         float* mb, float* vb, long long sP, int step, float lr, float beta1, float beta2,
+                         float eps, float grad_scale, int n_models, void* stream);
 
 /* ---- helpers for the tensor-core path ---------------------------------------------------------*/
 int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);

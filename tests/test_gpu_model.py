@@ -250,3 +250,25 @@ def test_engine_bf16_tensor_core_path_matches_oracle(dev, B):
                 got, refq = eng.view(name, eng.grad)[0], gq["d" + name]
                 assert rel_err(got, refq) < 2e-2 and rel_fro(got, refq) < 2e-2, (name, rel_err(got, refq), rel_fro(got, refq))
                 assert cos(got, ref32) > 0.995, (name, cos(got, ref32))
+
+
+def test_engine_fused_gradient_adam_is_bit_identical(dev):
+    """Small-batch sweep path: the Adam step with the weight gradients recomputed inside the optimiser kernel
+    (never written to HBM) gives bit-identical parameters and moments to linear_bwd_dw + flat Adam."""
+    from eeg_multimodal_b200 import HeadEngine
+
+    dims, B, M = (768, 768, 768), 8, 3
+    g = torch.Generator().manual_seed(0)
+    blocks = [torch.rand(B, d, generator=g).to(dev) for d in dims]
+    labels = (torch.rand(B, generator=g) < 0.66).long().to(dev)
+    engs = []
+    for fuse in (True, False):
+        e = HeadEngine(n_models=M, feature_dims=dims, eps=[0.1, 1.0, 8.0], seeds=[5, 980616, 77], lr=1e-3, precision="fp32")
+        e.fuse_adam = fuse
+        for _ in range(3):
+            st = e.train_step(blocks, labels)
+        engs.append((e, st))
+    (a, sa), (b, sb) = engs
+    assert torch.equal(a.flat, b.flat) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v)
+    assert torch.equal(a.DP, b.DP) and torch.equal(sa["loss"], sb["loss"])
+    assert not torch.equal(a.flat[0], a.flat[1])

@@ -28,12 +28,55 @@ def timeit(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+def sweep_main(a):
+    """Grouped fp32 small-batch kernels at the reference shapes: M models x (B=8, D=2304, H=768)."""
+    dev = torch.device("cuda:0")
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0}
+    M, B, D, H = a.sweep, 8, 2304, 768
+    P = D * D + D + H * D + H + 2 * H + 8
+    flat, m, v, gr = (torch.zeros(M, P, device=dev) for _ in range(4))
+    flat.uniform_(-0.02, 0.02)
+    W1, b1 = flat[:, :D * D].view(M, D, D), flat[:, D * D:D * D + D]
+    o2 = D * D + D
+    W2, b2 = flat[:, o2:o2 + H * D].view(M, H, D), flat[:, o2 + H * D:o2 + H * D + H]
+    mv = lambda t, off, shape: t[:, off:off + shape[0] * (shape[1] if len(shape) > 1 else 1)].view(M, *shape)
+    X = torch.rand(M, B, D, device=dev)
+    H1 = torch.rand(M, B, D, device=dev)
+    dZ1 = torch.randn(M, B, D, device=dev) * 1e-3
+    dZ2 = torch.randn(M, B, H, device=dev) * 1e-3
+    Y1, Y2, dX = torch.empty(M, B, D, device=dev), torch.empty(M, B, H, device=dev), torch.empty(M, B, D, device=dev)
+    cases = [
+        ("linear_fwd_W1", lambda: ops.linear_fwd(X, W1, b1, L.ACT_RELU, out=Y1), M * D * D * 4),
+        ("linear_fwd_W2", lambda: ops.linear_fwd(H1, W2, b2, L.ACT_TANH, out=Y2), M * H * D * 4),
+        ("linear_dx_W1", lambda: ops.linear_bwd_dx(dZ1, W1, out=dX), M * D * D * 4),
+        ("linear_dx_W2", lambda: ops.linear_bwd_dx(dZ2, W2, mask_src=H1, mask_mode=L.ACT_RELU, out=dX), M * H * D * 4),
+        ("linear_dw_W1", lambda: ops.linear_bwd_dw(dZ1, X, dW=mv(gr, 0, (D, D)), db=gr[:, D * D:D * D + D]), M * D * D * 4),
+        ("linear_adam_W1", lambda: ops.linear_adam_step(dZ1, X, W1, mv(m, 0, (D, D)), mv(v, 0, (D, D)), b1, m[:, D * D:D * D + D],
+                                                        v[:, D * D:D * D + D], 1), M * D * D * 24),
+        ("linear_adam_W2", lambda: ops.linear_adam_step(dZ2, H1, W2, mv(m, o2, (H, D)), mv(v, o2, (H, D)), b2,
+                                                        m[:, o2 + H * D:o2 + H * D + H], v[:, o2 + H * D:o2 + H * D + H], 1), M * H * D * 24),
+        ("adam_flat", lambda: ops.adam_step(flat, gr, m, v, 1), M * P * 28),
+    ]
+    for name, fn, nbytes in cases:
+        if a.only and a.only not in name:
+            continue
+        ms = timeit(fn, a.iters)
+        print(json.dumps({"kernel": name, "models": M, "ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1),
+                          "hbm_frac": round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 3)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--sweep", type=int, default=0, help="N models: time the grouped fp32 kernels of the B=8 sweep (D=2304) instead")
     a = ap.parse_args()
+    if a.sweep:
+        return sweep_main(a)
     dev = torch.device("cuda:0")
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
