@@ -65,6 +65,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.sm, self.power, self.reasons, self.stop_flag, self.max_sm = index, [], [], set(), False, None
         self.err = None
+        self.active = False   # the thread (and NVML) start before the warm-up; samples count only inside the timed region
 
     def run(self):
         try:
@@ -78,18 +79,22 @@ class ClockSampler(threading.Thread):
             names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
             while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                time.sleep(0.01)
+                if self.active:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                time.sleep(0.002)
         except Exception as e:  # no NVML: fall back to polling nvidia-smi (slower, fewer samples)
             self.err = repr(e)
             q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.002)
+                    continue
                 try:
                     out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                          capture_output=True, text=True, timeout=5).stdout.strip().split(",")
@@ -275,11 +280,12 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(W):
         step(i)
     fence()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.active = True
     _lib.launch_count = 0
     ops.TIMING = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,6 +298,7 @@ def run_ours(args):
     timing = ops.TIMING
     ops.TIMING = None
     ms = e0.elapsed_time(e1)
+    sampler.active = False
     sampler.stop_flag = True
     sampler.join(timeout=2)
     tms = torch.tensor([ms], device=dev, dtype=torch.float64)

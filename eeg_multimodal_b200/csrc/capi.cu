@@ -196,7 +196,6 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
   PGF_CHECK_ARG((epi >= 0 && epi <= 7) || epi == 9, "pgf_gemm_bf16: bad epilogue %d", epi);
   if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32 || epi == PGF_EPI_BIAS_TANH_F32)
     PGF_CHECK_ARG(bias && aligned16(bias), "pgf_gemm_bf16: epilogue needs a 16-byte aligned bias");
-  if (epi == PGF_EPI_RELUMASK_BF16) PGF_CHECK_ARG(aux && aligned16(aux) && (ld_aux % 8) == 0, "pgf_gemm_bf16: epilogue needs aux");
   GemmArgs g = {};
   g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.aux = aux; g.ld_aux = ld_aux; g.epi = epi;
   g.stream_k = stream_k; g.col_partial = col_partial;

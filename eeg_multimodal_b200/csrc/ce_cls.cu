@@ -59,10 +59,18 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     for (int i = threadIdx.x; i < 2 * nvec; i += CE_THREADS) s_w[i] = Wc[i];
     __syncthreads();
   }
-  float4 dw0[MODE == 2 ? NV : 1], dw1[MODE == 2 ? NV : 1], dsum[MODE == 2 ? NV : 1];
+  // MODE 2 accumulators: dWc rows in registers, the dz column sums in the warp's own shared-memory row
+  // (keeping all three sets in registers spills inside the row loop at the 128-register budget of 2 CTAs/SM)
+  float4 dw0[MODE == 2 ? NV : 1], dw1[MODE == 2 ? NV : 1];
+  float* s_dw = reinterpret_cast<float*>(s_dyn4 + 2 * nvec);  // [warps][3*H]: dWc row 0 | dWc row 1 | colsum(dz)
+  float* s_dsum = s_dw + warp * 3 * a.H + 2 * a.H;
   if (MODE == 2) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) dw0[k] = dw1[k] = dsum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < NV; ++k) {
+      dw0[k] = dw1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int col = (lane + 32 * k) << 2;
+      if (col < a.H) *reinterpret_cast<float4*>(s_dsum + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   const float b0 = a.bc[model * a.sbc], b1 = a.bc[model * a.sbc + 1];
   const long long* labels = a.labels ? a.labels + model * a.slab : nullptr;  // NULL: logits/pred only
@@ -141,7 +149,11 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
               d.z *= 1.f - h[k].z * h[k].z;
               d.w *= 1.f - h[k].w * h[k].w;
             }
-            if (MODE == 2) { dsum[k].x += d.x; dsum[k].y += d.y; dsum[k].z += d.z; dsum[k].w += d.w; }
+            if (MODE == 2) {
+              float4 acc = *reinterpret_cast<float4*>(s_dsum + (j << 2));
+              acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+              *reinterpret_cast<float4*>(s_dsum + (j << 2)) = acc;
+            }
             st4<DT>(a.dz, model * a.sdz + row * a.lddz + (j << 2), d);
           }
         }
@@ -170,7 +182,6 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     s_red[warp][2] = db0;
     s_red[warp][3] = db1;
   }
-  float* s_dw = reinterpret_cast<float*>(s_dyn4 + 2 * nvec);
   if (MODE == 2) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -178,7 +189,6 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
       if (col < a.H) {
         *reinterpret_cast<float4*>(s_dw + warp * 3 * a.H + col) = dw0[k];
         *reinterpret_cast<float4*>(s_dw + warp * 3 * a.H + a.H + col) = dw1[k];
-        *reinterpret_cast<float4*>(s_dw + warp * 3 * a.H + 2 * a.H + col) = dsum[k];
       }
     }
   }

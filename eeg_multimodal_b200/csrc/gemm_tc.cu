@@ -30,7 +30,7 @@ namespace pgf {
 #define PGF_EPI_STORE_BF16 0        // C = acc
 #define PGF_EPI_BIAS_RELU_BF16 1    // C = relu(acc + bias[n])
 #define PGF_EPI_BIAS_TANH_BF16 2    // C = tanh(acc + bias[n])
-#define PGF_EPI_RELUMASK_BF16 3     // C = acc * (aux[m,n] > 0)          (aux bf16 [M,N])
+#define PGF_EPI_RELUMASK_BF16 3     // retired (bf16 mask-source tile); use PGF_EPI_BITMASK_BF16
 #define PGF_EPI_ATOMIC_F32 4        // C(fp32) += acc                    (stream-K partials)
 #define PGF_EPI_STORE_F32 5         // C(fp32) = acc
 #define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
@@ -39,7 +39,7 @@ namespace pgf {
 #define PGF_EPI_BITMASK_BF16 9      // C = acc * bit(aux, m, n)          (aux uint32 [M, N/32]: ReLU sign bits written by epi 1)
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;  // BM = accumulator rows per CTA (TMEM lanes)
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps
 // CG = CTAs per MMA (tcgen05 cta_group).  CG=2: a CTA pair (cluster of 2, one TPC) owns a 256x256
 // tile; each CTA stages its own 128 A rows and HALF of the B tile, the MMA reads both halves, so
 // shared-memory fill traffic per flop drops by a third and the ring gets 6 stages instead of 4.
@@ -48,9 +48,8 @@ template <int CG> struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;     // 32 KB (CG=1) / 16 KB (CG=2)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = CG == 1 ? 3 : 5;
-  static constexpr int EPI_BYTES = 4 * 16384;  // 2 output staging + 2 mask-source staging buffers, [128 rows][128 B] each
-  static constexpr int CS_BYTES = 1024;        // per-warp column sums of one 64-column group, [4 warps][64]
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + CS_BYTES;
+  static constexpr int EPI_BYTES = 4 * 16384;  // 2 epilogue groups x 2 output staging buffers, [128 rows][128 B] each
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -152,6 +151,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+        "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+        "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+        "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  Field layout as in the PTX ISA
 // "tcgen05 shared memory descriptor": start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version [46,48), layout_type [61,64) (2 = 128B swizzle).
@@ -229,12 +247,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
 template <bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmArgs g) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using C = Cfg<CG>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_STAGE_BYTES = C::A_BYTES;
   constexpr int TILE_M = BM * CG, BN_CTA = BN / CG;
@@ -244,12 +261,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;  // out staging [2][16 KB], mask staging [2][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + STAGES * STAGE_BYTES + C::EPI_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4..2S+6) aux_full, tmem slot
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, tmem slot
   const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES), tempty_bar = smem_u32(bars + 2 * STAGES + 2);
-  const uint32_t auxfull_bar = smem_u32(bars + 2 * STAGES + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
-  float* s_cs = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES + C::EPI_BYTES + 256);  // [4][64]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb_n = (g.N + BN - 1) / BN;
@@ -266,8 +281,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 4 * CG);  // one arrival per epilogue warp of the group
-      mbar_init(auxfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 8 * CG);  // one arrival per epilogue warp of the MMA group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -360,20 +374,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5, every CTA) ===============================
-    // TMEM -> registers -> (bias / activation / ReLU mask) -> 128B-swizzled shared staging -> TMA store
+    // =============================== epilogue (warps 2..9, every CTA) ===============================
+    // TMEM -> registers -> (bias / activation / ReLU sign bits) -> 128B-swizzled shared staging -> TMA store
     // (or TMA fp32 add-reduction for split-K partials).  The thread <-> accumulator-row mapping of
     // tcgen05.ld would make direct global stores touch 32 different lines per instruction; staging
-    // through shared memory hands the global traffic to the TMA engine in full 128-byte rows, and the
-    // ReLU-mask source tile arrives the same way (TMA load, one group ahead).
+    // through shared memory hands the global traffic to the TMA engine in full 128-byte rows.
+    // Two epilogue groups (EG) of four warps: a warp may only read the TMEM lane quarter (warp % 4), so each
+    // group covers all 128 accumulator rows, and the groups take alternate column groups of the tile --
+    // two warps per SM sub-partition keep the short-K GEMMs (whose epilogue outweighs their 12 k-blocks of
+    // MMAs) and the Philox-regenerating dDP epilogue off the critical path.  Each group owns two staging
+    // buffers, one named barrier and one TMA-store leader; one barrier per column group (the leader waits
+    // for the previous store's shared-memory reads before arriving, which frees the other buffer).
+    const int eg = (warp - 2) >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    const bool leader_thread = (warp == 2 && lane == 0);
+    const bool leader_thread = ((warp - 2) & 3) == 0 && lane == 0;
+    const uint32_t bar_id = 1u + static_cast<uint32_t>(eg);
     const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
                          g.epi == PGF_EPI_BIAS_TANH_F32;
     const bool has_bias = g.epi == PGF_EPI_BIAS_RELU_BF16 || g.epi == PGF_EPI_BIAS_TANH_BF16 || g.epi == PGF_EPI_BIAS_F32 ||
                           g.epi == PGF_EPI_BIAS_TANH_F32;
-    const bool has_aux = g.epi == PGF_EPI_RELUMASK_BF16;
     // ReLU sign bits, one uint32 per (row, 32 columns): written by the forward epilogue, read back by the
     // backward one -- 1/16 of the bytes of the bf16 activation tile the mask would otherwise be derived from
     const bool mask_out = g.epi == PGF_EPI_BIAS_RELU_BF16 && g.aux != nullptr;
@@ -381,11 +401,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* mask_words = static_cast<uint32_t*>(const_cast<void*>(g.aux));
     const bool want_cs = g.col_partial != nullptr && !out_f32;
     const int GW = out_f32 ? 32 : 64;  // columns per 128-byte staging row
+    const uint32_t stage_base = epi_base + static_cast<uint32_t>(eg) * 32768u;
+    const int neg = g.epi_groups;  // 2, or 1 = only the first group works (tuning knob; idle warps just release TMEM)
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     Scheduler sched(g, TILE_M, worker, nworkers);
     WorkUnit u;
-    uint32_t unit = 0, gcount = 0, aux_issued = 0, aux_used = 0;
+    uint32_t unit = 0, gcount = 0;
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(tempty_bar, 0) : tempty_bar;
     while (sched.next(u)) {
       const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
@@ -399,13 +421,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      // column partials (bias gradient / dDP): one row per 32-row accumulator slab = per warp, no cross-warp step
+      float* cp_row = g.col_partial ? g.col_partial + (static_cast<long long>(m0 >> 5) + quarter) * g.N : nullptr;
       if (g.epi == PGF_EPI_DDP_PARTIAL) {
         // dX tile never leaves the SM: multiply by the regenerated Laplace noise of (global row, column) and
-        // reduce over the 128 accumulator rows; one 1 KB row of column partials per (128-row slab, N tile).
-        float* cs = reinterpret_cast<float*>(smem_al + STAGES * STAGE_BYTES) + (unit & 1) * (4 * BN);  // [4 warps][256]
+        // reduce over the warp's 32 accumulator rows.
         const uint32_t grow = static_cast<uint32_t>(g.row0 + static_cast<unsigned long long>(m0 + row));
 #pragma unroll 1
-        for (int n = n0; n < n0 + BN && n < g.N; n += 32) {
+        for (int n = n0 + 32 * eg; eg < neg && n < n0 + BN && n < g.N; n += 32 * neg) {
           uint32_t v[32];
           tmem_ld32(taddr + (n - n0), v);
           float f[32];
@@ -417,43 +440,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) * laplace_from_bits(r.z);
             f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) * laplace_from_bits(r.w);
           }
-          cs[quarter * BN + (n - n0) + lane] = warp_colsum32(f, lane);
+          const float cs = warp_colsum32(f, lane);
+          if (n + lane < g.N) cp_row[n + lane] = cs;
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // accumulator fully read: hand TMEM back early
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
           else mbar_arrive(tempty_bar + 8 * acc);
         }
-        epi_bar_sync();  // one barrier per tile: `cs` is double-buffered on the tile parity
-        float* dst = g.col_partial + static_cast<long long>(m0 / BM) * g.N + n0;
-        for (int c = row; c < BN && n0 + c < g.N; c += 128)
-          dst[c] = (cs[c] + cs[BN + c]) + (cs[2 * BN + c] + cs[3 * BN + c]);
         ++unit;
         continue;
       }
-      if (has_aux && leader_thread) {  // mask tile of the first group
-        const uint32_t b = aux_issued & 1;
-        mbar_expect_tx(auxfull_bar + 8 * b, 16384);
-        tma_load_2d<1>(epi_base + 32768 + b * 16384, &tmAux, auxfull_bar + 8 * b, n0, m0);
-      }
-      if (has_aux) ++aux_issued;
 #pragma unroll 1
-      for (int n = n0; n < n0 + BN && n < g.N; n += GW) {  // warp-uniform
-        const uint32_t sbuf = epi_base + (gcount & 1) * 16384;
-        // the store issued two groups ago has finished reading this staging buffer
-        if (leader_thread) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        epi_bar_sync();
-        if (has_aux) {
-          if (n + GW < n0 + BN && n + GW < g.N) {  // prefetch the next group's mask tile
-            if (leader_thread) {
-              const uint32_t b = aux_issued & 1;
-              mbar_expect_tx(auxfull_bar + 8 * b, 16384);
-              tma_load_2d<1>(epi_base + 32768 + b * 16384, &tmAux, auxfull_bar + 8 * b, n + GW, m0);
-            }
-            ++aux_issued;
-          }
-        }
+      for (int n = n0 + GW * eg; eg < neg && n < n0 + BN && n < g.N; n += neg * GW) {  // warp-uniform
+        const uint32_t sbuf = stage_base + (gcount & 1) * 16384;
         uint32_t mw[2] = {0u, 0u};
         if (out_f32) {
           uint32_t v[32];
@@ -482,23 +483,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                          : "memory");
           }
         } else {
-          const uint32_t abuf = epi_base + 32768 + (aux_used & 1) * 16384;
           if (mask_in) {
             const int gi = (n - n0) >> 6;  // 64-column group inside the tile
             mw[0] = gi == 0 ? mwa.x : (gi == 1 ? mwa.z : (gi == 2 ? mwb.x : mwb.z));
             mw[1] = gi == 0 ? mwa.y : (gi == 1 ? mwa.w : (gi == 2 ? mwb.y : mwb.w));
           }
-          if (has_aux) {
-            mbar_wait(auxfull_bar + 8 * (aux_used & 1), (aux_used >> 1) & 1);
-            ++aux_used;
-          }
+          uint32_t v[64];
+          tmem_ld64(taddr + (n - n0), v);  // the whole 64-column group in one TMEM load
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32(taddr + (n - n0) + 32 * half, v);
             float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[32 * half + i]);
             if (has_bias) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -524,19 +520,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint32_t m = mw[half];
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = (m & (1u << i)) ? f[i] : 0.f;
-            } else if (has_aux) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t src = abuf + row_off + ((static_cast<uint32_t>(4 * half + c) ^ swz) << 4);
-                uint32_t w[4];
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 h = unpack_bf16x2(w[j]);
-                  f[8 * c + 2 * j] = h.x > 0.f ? f[8 * c + 2 * j] : 0.f;
-                  f[8 * c + 2 * j + 1] = h.y > 0.f ? f[8 * c + 2 * j + 1] : 0.f;
-                }
-              }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -547,22 +530,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            : "memory");
             }
             // fused bias gradient: column sums of the (fp32) epilogue values over this warp's 32 rows
-            if (want_cs) s_cs[quarter * 64 + 32 * half + lane] = warp_colsum32(f, lane);
+            if (want_cs) {
+              const float cs = warp_colsum32(f, lane);
+              if (n + 32 * half + lane < g.N) cp_row[n + 32 * half + lane] = cs;
+            }
           }
         }
-        if (mask_out && m0 + row < g.M && n < g.N)
+        if (mask_out && m0 + row < g.M)
           *reinterpret_cast<uint2*>(mask_words + static_cast<long long>(m0 + row) * g.ld_aux + (n >> 5)) = make_uint2(mw[0], mw[1]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to TMA
-        epi_bar_sync();
+        // the previous store of this group has finished reading its staging buffer (= the one the next column group
+        // will overwrite); arriving at the barrier below publishes that to the other three warps
+        if (leader_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (leader_thread) {
           if (g.epi == PGF_EPI_ATOMIC_F32) tma_reduce_add_2d(&tmC, sbuf, n, m0);
           else tma_store_2d(&tmC, sbuf, n, m0);  // rows >= M / columns >= N are clipped by the tensor map
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        // combine the 4 warps' column sums of this group (the next group's s_cs writes come after its first barrier)
-        if (want_cs && row < 64 && n + row < g.N)
-          g.col_partial[static_cast<long long>(m0 / BM) * g.N + n + row] =
-              (s_cs[row] + s_cs[64 + row]) + (s_cs[128 + row] + s_cs[192 + row]);
         ++gcount;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -631,6 +616,10 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
               cudaStream_t s) {
   GemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PGF_OK;
+  if (g.epi == PGF_EPI_RELUMASK_BF16) {
+    set_error("pgf_gemm_bf16: the bf16 mask-source epilogue (3) was retired; write the ReLU sign bits with epilogue 1 and apply them with epilogue 9");
+    return PGF_ERR_UNSUPPORTED;
+  }
   const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
                        g.epi == PGF_EPI_BIAS_TANH_F32;
   if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.epi != PGF_EPI_DDP_PARTIAL && (g.ldc % (out_f32 ? 4 : 8))) ||
@@ -638,7 +627,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     set_error("pgf_gemm_bf16: N, lda, ldb must be multiples of 8, ldc of 8 (bf16 out) / 4 (fp32 out), pointers 16-byte aligned");
     return PGF_ERR_ARG;
   }
-  CUtensorMap tmA, tmB, tmC, tmAux;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   // output staging rows are 128 bytes: 64 bf16 or 32 fp32 columns x 128 accumulator rows per TMA store
   const bool no_c = g.epi == PGF_EPI_DDP_PARTIAL;
@@ -666,12 +655,6 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   } else {
     rc = make_tmap(&tmC, g.C, g.M, g.N, g.ldc, out_f32 ? 32 : 64, BM, out_f32);
     if (rc != PGF_OK) return rc;
-  }
-  if (g.epi == PGF_EPI_RELUMASK_BF16) {
-    rc = make_tmap(&tmAux, g.aux, g.M, g.N, g.ld_aux, 64, BM);
-    if (rc != PGF_OK) return rc;
-  } else {
-    tmAux = tmC;
   }
   static const bool force_1cta_b = getenv("PGF_GEMM_1CTA") != nullptr;
   const int cg_b = (!force_1cta_b && g.M > BM) ? 2 : 1;
@@ -708,6 +691,8 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     const long long units = static_cast<long long>(tiles) * best;
     workers = static_cast<int>(units < workers_max ? units : workers_max);
   }
+  static const bool one_epi_group = getenv("PGF_GEMM_EPI_GROUPS") != nullptr && getenv("PGF_GEMM_EPI_GROUPS")[0] == '1';
+  g.epi_groups = one_epi_group ? 1 : 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(workers * cg);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -725,7 +710,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     cfg.dynamicSmemBytes = Cfg<CGV>::SMEM_BYTES;                                                                          \
     cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
                          Cfg<CGV>::SMEM_BYTES);                                                                           \
-    lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, tmC, tmAux, g);                                      \
+    lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, tmC, g);                                      \
   } while (0)
 #define PGF_GEMM_DISPATCH(CGV)                               \
   do {                                                       \
@@ -746,13 +731,13 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   return PGF_OK;
 }
 
-// rows of the column-partial workspace for an M-row output: one per 128-row accumulator slab that a CTA owns
+// rows of the column-partial workspace for an M-row output: one per 32-row accumulator slab (= per epilogue warp)
 int gemm_partial_rows(int M) {
   if (M <= 0) return 0;
   static const bool force_1cta = getenv("PGF_GEMM_1CTA") != nullptr;
   const int cg = (!force_1cta && M > BM) ? 2 : 1;
   const int tile_m = BM * cg;
-  return ((M + tile_m - 1) / tile_m) * cg;
+  return ((M + tile_m - 1) / tile_m) * (tile_m / 32);
 }
 
 }  // namespace pgf

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (NOISE == PGF_NOISE_PHILOX)
-            f[e] = __fsub_rn(f[e], mn);  // scaled by 1/range inside the fused multiply-add below
+            f[e] = __fmul_rn(__fsub_rn(f[e], mn), inv_range);
           else
             f[e] = __fdiv_rn(__fsub_rn(f[e], mn), range);
         }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
                                     : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(f[e], inv_range, laplace_scaled_from_bits(rb[e], eh[e]));
+          for (int e = 0; e < 4; ++e) f[e] = perturb_fma(f[e], rb[e], eh[e]);
           if (WANT_GATE) {
             // The two mask planes sum to one (hard: exactly, soft: within 1 ulp), so the gated
             // value IS the perturbed value; only the gate index is a real output.
@@ -341,13 +341,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_kernel(const 
       if (j < nvec) {
         float f[4] = {__fsub_rn(v[k].x, mn), __fsub_rn(v[k].y, mn), __fsub_rn(v[k].z, mn), __fsub_rn(v[k].w, mn)};
         if (NOISE == PGF_NOISE_PHILOX) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f[e] = __fmul_rn(f[e], inv_range);
           const float4 e4 = s_eps[j];
           const float eh[4] = {e4.x, e4.y, e4.z, e4.w};  // = -ln2 * eps_hat
           const uint4 r = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, a.rk)
                                     : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) f[e] = __fmaf_rn(f[e], inv_range, laplace_scaled_from_bits(rb[e], eh[e]));
+          for (int e = 0; e < 4; ++e) f[e] = perturb_fma(f[e], rb[e], eh[e]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] = __fdiv_rn(f[e], range);
@@ -356,6 +358,138 @@ __global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_kernel(const 
       }
     }
   }
+}
+
+// Shared-batch variant: every model of an eps x seed sweep perturbs the SAME feature rows (the reference sweep
+// re-reads one dataset per run), so a row is fetched, min/max-reduced and normalised once and then perturbed
+// once per model with that model's eps_hat row (L1-resident) and Philox key: per model-row the kernel reads
+// 4*D/n_models and writes 2*D (bf16) bytes, and the load / reduction / normalisation instructions are amortised.
+template <int NV, typename OutT, int RING_STAGES>
+__global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_shared_kernel(const PerturbFwdArgs a) {
+  extern __shared__ float4 smem4[];
+  __shared__ float s_part[2][FWD_THREADS / 32][3];
+  __shared__ __align__(8) unsigned long long s_full[RING_STAGES];
+  const int nvec = a.D >> 2;
+  float4* s_rows = smem4;  // [RING_STAGES][D/4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < RING_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t row_bytes = static_cast<uint32_t>(a.D) * 4u;
+  auto issue = [&](int it) {
+    const long long row = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
+    if (row >= a.B) return;
+    const int st = it % RING_STAGES;
+    const uint32_t bar = smem_addr_u32(&s_full[st]);
+    const uint32_t dst = smem_addr_u32(s_rows + st * nvec);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+    uint32_t off = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      if (a.d[b] > 0) {
+        const float* src = a.x[b] + row * a.ld[b];
+        const uint32_t nbytes = static_cast<uint32_t>(a.d[b]) * 4u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(src), "r"(nbytes), "r"(bar)
+                     : "memory");
+        off += nbytes;
+      }
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int it = 0; it < RING_STAGES - 1; ++it) issue(it);
+  }
+  int it = 0;
+  for (long long row = blockIdx.x; row < a.B; row += gridDim.x, ++it) {
+    const int st = it % RING_STAGES;
+    ring_mbar_wait(smem_addr_u32(&s_full[st]), static_cast<uint32_t>(it / RING_STAGES) & 1u);
+    float4 v[NV];
+    float mn = INFINITY, mx = -INFINITY, probe = 0.f;
+    const float4* srow = s_rows + st * nvec;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = tid + FWD_THREADS * k;
+      if (j < nvec) {
+        v[k] = srow[j];
+        mn = fminf(fminf(mn, v[k].x), fminf(v[k].y, fminf(v[k].z, v[k].w)));
+        mx = fmaxf(fmaxf(mx, v[k].x), fmaxf(v[k].y, fmaxf(v[k].z, v[k].w)));
+        probe += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    probe = warp_sum(probe);
+    float(*part)[3] = s_part[it & 1];
+    if (lane == 0) {
+      part[warp][0] = mn;
+      part[warp][1] = mx;
+      part[warp][2] = probe;
+    }
+    __syncthreads();
+    if (tid == 0) issue(it + RING_STAGES - 1);
+#pragma unroll
+    for (int w = 0; w < FWD_THREADS / 32; ++w) {
+      mn = fminf(mn, part[w][0]);
+      mx = fmaxf(mx, part[w][1]);
+    }
+    probe = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
+    if (probe != probe) mn = mx = __int_as_float(0x7fc00000);
+    const float inv_range = __frcp_rn(__fsub_rn(mx, mn));
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {  // normalised once, perturbed once per model
+      v[k].x = __fmul_rn(__fsub_rn(v[k].x, mn), inv_range);
+      v[k].y = __fmul_rn(__fsub_rn(v[k].y, mn), inv_range);
+      v[k].z = __fmul_rn(__fsub_rn(v[k].z, mn), inv_range);
+      v[k].w = __fmul_rn(__fsub_rn(v[k].w, mn), inv_range);
+    }
+    const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+#pragma unroll 1
+    for (int m = 0; m < a.n_models; ++m) {
+      const unsigned long long seed = a.model_seeds ? a.model_seeds[m] : a.seed + static_cast<unsigned long long>(m) * a.seed_step;
+      const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
+      const float4* ge = reinterpret_cast<const float4*>(a.eps_hat + m * a.s_coef);
+      char* outp = static_cast<char*>(a.out) + m * a.s_out * static_cast<long long>(sizeof(OutT));
+      if (tid == 0) {
+        if (a.row_min) a.row_min[static_cast<long long>(m) * a.B + row] = mn;
+        if (a.row_max) a.row_max[static_cast<long long>(m) * a.B + row] = mx;
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int j = tid + FWD_THREADS * k;
+        if (j < nvec) {
+          const float4 e4 = __ldg(ge + j);
+          const uint4 r = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
+          float4 o;
+          o.x = perturb_fma(v[k].x, r.x, __fmul_rn(e4.x, -0.69314718055994531f));
+          o.y = perturb_fma(v[k].y, r.y, __fmul_rn(e4.y, -0.69314718055994531f));
+          o.z = perturb_fma(v[k].z, r.z, __fmul_rn(e4.z, -0.69314718055994531f));
+          o.w = perturb_fma(v[k].w, r.w, __fmul_rn(e4.w, -0.69314718055994531f));
+          store_out4<OutT>(outp, row * a.ld_out + (j << 2), o);
+        }
+      }
+    }
+  }
+}
+
+template <int NV, typename OutT>
+static int launch_fwd_ring_shared(const PerturbFwdArgs& a, cudaStream_t stream) {
+  constexpr int S = 3;
+  const size_t smem = static_cast<size_t>(a.D) * sizeof(float) * S;
+  auto kern = perturb_fwd_ring_shared_kernel<NV, OutT, S>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FWD_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+  int gx = num_sms() * occ;
+  if (gx > a.B) gx = a.B;
+  kern<<<gx, FWD_THREADS, smem, stream>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_fwd(shared ring)");
+  return PGF_OK;
 }
 
 template <int NV, int NOISE, typename OutT, int RING_STAGES>
@@ -450,8 +584,17 @@ int perturb_gate_fwd(const PerturbFwdArgs& a_in, int noise, int out_dtype, bool 
   a.rk = philox_make_keys(a.seed);
   // Large batches: one launch per model, so the Philox round keys are compile-time-indexed kernel
   // arguments (constant-bank operands).  Small batches (the B=8 sweep): one grouped launch.
-  const bool split = noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate && !a.model_seeds &&
-                     static_cast<long long>(a.B) * a.D >= (1LL << 22);
+  const bool big = static_cast<long long>(a.B) * a.D >= (1LL << 22);
+  static const bool no_ring = getenv("PGF_PERTURB_NO_RING") != nullptr;
+  if (!no_ring && noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate && big && a.sx[0] == 0 && a.sx[1] == 0 && a.sx[2] == 0) {
+    // one batch shared by the whole sweep: fetch / normalise each row once, perturb it once per model
+    const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
+    const bool f32 = out_dtype == PGF_DT_F32;
+    if (nv <= 2) return f32 ? launch_fwd_ring_shared<2, float>(a, s) : launch_fwd_ring_shared<2, __nv_bfloat16>(a, s);
+    if (nv <= 5) return f32 ? launch_fwd_ring_shared<5, float>(a, s) : launch_fwd_ring_shared<5, __nv_bfloat16>(a, s);
+    if (nv <= 8) return f32 ? launch_fwd_ring_shared<8, float>(a, s) : launch_fwd_ring_shared<8, __nv_bfloat16>(a, s);
+  }
+  const bool split = noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate && !a.model_seeds && big;
   if (!split) return perturb_gate_fwd_one(a, noise, out_dtype, want_gate, s);
   const size_t esz = out_dtype == PGF_DT_F32 ? 4 : 2;
   for (int m = 0; m < a_in.n_models; ++m) {
@@ -569,12 +712,14 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
   *reinterpret_cast<float4*>(a.partial + (static_cast<long long>(model) * a.nslab + slab) * a.D + col) = acc;
 }
 
-// Deterministic column reduction of a [nslab, D] partial buffer: a CTA owns 32 columns, its 8 warps take
+// Deterministic column reduction of a [nslab, D] partial buffer: a CTA owns 32 columns, its warps take
 // interleaved slabs (4 loads in flight each), then combine in a fixed order.
-__global__ void __launch_bounds__(256) perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
-                                                                      const float* __restrict__ coef, long long s_coef,
-                                                                      float* __restrict__ dDP, long long s_dDP, float accumulate) {
-  __shared__ float s_part[8][32];
+constexpr int FIN_WARPS = 32;
+__global__ void __launch_bounds__(FIN_WARPS * 32) perturb_bwd_dp_finalize_kernel(const float* __restrict__ partial, int nslab, int D,
+                                                                                const float* __restrict__ coef, long long s_coef,
+                                                                                float* __restrict__ dDP, long long s_dDP,
+                                                                                float accumulate) {
+  __shared__ float s_part[FIN_WARPS][32];
   const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int d = blockIdx.x * 32 + lane;
   const int model = blockIdx.y;
@@ -582,20 +727,20 @@ __global__ void __launch_bounds__(256) perturb_bwd_dp_finalize_kernel(const floa
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (d < D) {
     int i = rg;
-    for (; i + 24 < nslab; i += 32) {
+    for (; i + 3 * FIN_WARPS < nslab; i += 4 * FIN_WARPS) {
       s0 += P[static_cast<long long>(i) * D];
-      s1 += P[static_cast<long long>(i + 8) * D];
-      s2 += P[static_cast<long long>(i + 16) * D];
-      s3 += P[static_cast<long long>(i + 24) * D];
+      s1 += P[static_cast<long long>(i + FIN_WARPS) * D];
+      s2 += P[static_cast<long long>(i + 2 * FIN_WARPS) * D];
+      s3 += P[static_cast<long long>(i + 3 * FIN_WARPS) * D];
     }
-    for (; i < nslab; i += 8) s0 += P[static_cast<long long>(i) * D];
+    for (; i < nslab; i += FIN_WARPS) s0 += P[static_cast<long long>(i) * D];
   }
   s_part[rg][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (rg == 0 && d < D) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += s_part[w][lane];
+    for (int w = 0; w < FIN_WARPS; ++w) s += s_part[w][lane];
     const float v = coef ? s * coef[model * s_coef + d] : s;
     float* o = dDP + model * s_dDP + d;
     *o = accumulate != 0.f ? *o + v : v;
@@ -604,7 +749,7 @@ __global__ void __launch_bounds__(256) perturb_bwd_dp_finalize_kernel(const floa
 
 // out[n] = (coef ? coef[n] : 1) * sum_r partial[r][n], fixed summation order (the column partials of the GEMM epilogues)
 int reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate, cudaStream_t s) {
-  perturb_bwd_dp_finalize_kernel<<<dim3((N + 31) / 32, 1), 256, 0, s>>>(partial, rows, N, coef, 0, out, 0, accumulate ? 1.f : 0.f);
+  perturb_bwd_dp_finalize_kernel<<<dim3((N + 31) / 32, 1), FIN_WARPS * 32, 0, s>>>(partial, rows, N, coef, 0, out, 0, accumulate ? 1.f : 0.f);
   PGF_CUDA_LAUNCH_CHECK("pgf_reduce_partials");
   return PGF_OK;
 }
@@ -664,7 +809,7 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
   const dim3 fgrid((D + 31) / 32, n_models);
-  perturb_bwd_dp_finalize_kernel<<<fgrid, 256, 0, s>>>(workspace, slabs, D, coef, s_coef, dDP, s_dDP, accumulate ? 1.f : 0.f);
+  perturb_bwd_dp_finalize_kernel<<<fgrid, FIN_WARPS * 32, 0, s>>>(workspace, slabs, D, coef, s_coef, dDP, s_dDP, accumulate ? 1.f : 0.f);
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp(finalize)");
   return PGF_OK;
 }

@@ -90,6 +90,17 @@ __device__ __forceinline__ float laplace_scaled_from_bits(uint32_t r, float c) {
   asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(cs) : "r"(__float_as_uint(c)), "r"(r), "r"(0x80000000u));
   return lg2_ftz(v) * __uint_as_float(cs);
 }
+// Perturbed feature as ONE fused multiply-add on top of the normalised value xn:
+//   xn + eps_hat * Laplace(r)  =  lg2(v) * (c ^ sign(r)) + xn,   c = -ln2 * eps_hat.
+// Every Philox-mode forward kernel uses exactly this sequence, so grouped, single-model and TMA-ring launches
+// are bit-identical.
+__device__ __forceinline__ float perturb_fma(float xn, uint32_t r, float c) {
+  uint32_t one_m, cs;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(one_m) : "r"(r), "r"(0x7FFFFFu), "r"(0x3F800000u));
+  asm("lop3.b32 %0, %1, %2, %3, 0x78;" : "=r"(cs) : "r"(__float_as_uint(c)), "r"(r), "r"(0x80000000u));
+  const float v = __uint_as_float(one_m) - 0.99999994039535522f;
+  return __fmaf_rn(lg2_ftz(v), __uint_as_float(cs), xn);
+}
 __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
   return laplace_scaled_from_bits(r, -0.69314718055994531f);
 }

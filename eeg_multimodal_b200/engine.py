@@ -37,6 +37,9 @@ class HeadEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("HeadEngine needs a CUDA device: there is no CPU fallback")
         assert precision in ("fp32", "bf16")
+        if precision == "bf16" and sum(int(d) for d in feature_dims) % 128:
+            raise ValueError("the bf16 tensor-core path packs the ReLU sign bits in 128-bit rows: the fused width must be a "
+                             "multiple of 128 (2304 and 2560 are); use precision='fp32' for other widths")
         self.M = int(n_models)
         self.dims = tuple(int(d) for d in feature_dims)
         self.D, self.H, self.C = sum(self.dims), int(hidden), 2
@@ -159,10 +162,12 @@ class HeadEngine:
         elif self.seed_step is not None:   # one grouped launch for the whole ensemble
             ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, seed=self.seeds[0],
                                  seed_step=self.seed_step, offset=offset, row0=row0, tau=self.tau, hard=hard, out=out, n_models=M)
-        elif blocks[0].shape[-2] * self.D < (1 << 22):   # small batches: one grouped launch, seeds from the device array
+        elif blocks[0].shape[-2] * self.D < (1 << 22) or all(b.dim() == 2 for b in blocks):
+            # one grouped launch, seeds from the device array: small batches (B=8 sweep), or a large batch SHARED by
+            # the sweep (each row fetched and normalised once, perturbed once per model)
             ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, model_seeds=self.seeds_dev, offset=offset,
                                  row0=row0, tau=self.tau, hard=hard, out=out, n_models=M)
-        else:                                            # large batches: per-model launches of the TMA-ring kernel
+        else:                                            # large per-model batches: one TMA-ring launch per model
             for i in range(M):
                 bl = [b[i] if b.dim() == 3 else b for b in blocks]
                 ops.perturb_gate_fwd(bl, coef[0, i], coef[1, i], noise_mode=L.NOISE_PHILOX, seed=self.seeds[i], offset=offset,
@@ -238,8 +243,8 @@ class HeadEngine:
         H1 = self._buf("H1h", (M, B, D), bf)
         H2 = self._buf("H2f", (M, B, H), torch.float32)  # tanh output kept in fp32: exact logits / loss
         W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
-        # ReLU sign bits (1 bit per activation) for the backward mask, when the width allows 128-bit mask rows
-        bits = self._buf("relu_bits", (M, B, D // 32), torch.int32) if (backward and D % 128 == 0) else None
+        # ReLU sign bits (1 bit per activation) for the backward mask
+        bits = self._buf("relu_bits", (M, B, D // 32), torch.int32) if backward else None
         for i in range(M):
             ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i],
                           aux=None if bits is None else bits[i])
@@ -257,8 +262,7 @@ class HeadEngine:
         for i in range(M):
             # dZ1 = (dZ2 . W2) * relu'(H1):   B operand = W2 stored [K=H, N=D]  -> MN-major.  In pass 2 the bias
             # gradient db1 = colsum(dZ1) is reduced inside the epilogue.
-            ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True,
-                          epi=L.EPI_RELUMASK_BF16 if bits is None else L.EPI_BITMASK_BF16, aux=H1[i] if bits is None else bits[i],
+            ops.gemm_bf16(dZ2[i], W2h[i], dZ1[i], M=B, N=D, K=H, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits[i],
                           colsum_out=gb1[i] if mode == "model" else None)
         if mode == "dp":
             inj, offset = nspec

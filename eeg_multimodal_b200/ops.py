@@ -252,12 +252,10 @@ def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16,
     """C[M,N] = A . B^T on tcgen05 (bf16 in, fp32 accumulate in TMEM) with a fused epilogue.
     colsum_out [N] (bf16-output epilogues): also the column sums of the fp32 epilogue values, i.e. the
     bias gradient when C is a pre-activation gradient -- reduced per 128-row slab inside the epilogue.
-    aux: EPI_RELUMASK_BF16: bf16 [M,N] mask source; EPI_BIAS_RELU_BF16 (optional, OUT) / EPI_BITMASK_BF16 (IN):
-    int32 [M, N/32] ReLU sign bits."""
+    aux: int32 [M, N/32] ReLU sign bits -- EPI_BIAS_RELU_BF16 writes them (optional), EPI_BITMASK_BF16 applies them."""
     _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B"); _chk(C, None, "C")
     if aux is not None:
-        want = torch.bfloat16 if epi == L.EPI_RELUMASK_BF16 else torch.int32  # mask source tile | packed ReLU sign bits
-        _chk(aux, want, "aux")
+        _chk(aux, torch.int32, "aux")   # packed ReLU sign bits
     part = None
     if colsum_out is not None:
         rows = L.query("pgf_gemm_partial_rows", M)

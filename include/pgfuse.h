@@ -40,7 +40,7 @@ extern "C" {
 #define PGF_EPI_STORE_BF16 0
 #define PGF_EPI_BIAS_RELU_BF16 1
 #define PGF_EPI_BIAS_TANH_BF16 2
-#define PGF_EPI_RELUMASK_BF16 3
+#define PGF_EPI_RELUMASK_BF16 3 /* retired: returns PGF_ERR_UNSUPPORTED (superseded by the sign-bit mask, 9) */
 #define PGF_EPI_ATOMIC_F32 4
 #define PGF_EPI_STORE_F32 5
 #define PGF_EPI_BIAS_F32 6
@@ -130,14 +130,15 @@ int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float
  * C[M,N] = A[M,K] . B[N,K]^T, bf16 operands, fp32 accumulation in TMEM, fused epilogue `epi`.
  * a_mn / b_mn != 0: that operand is stored transposed ([K,M] / [K,N] row-major), as the
  * weight-gradient GEMMs need.  stream_k != 0 (with PGF_EPI_ATOMIC_F32, C zeroed by the caller)
- * splits K across CTAs.  bias [N] fp32; aux [M,N] bf16 (ReLU mask source); col_partial: below.  */
+ * splits K across CTAs.  bias [N] fp32; aux: uint32 [M, ld_aux >= N/32] ReLU sign bits (N % 128 == 0):
+ * OUT (optional) for PGF_EPI_BIAS_RELU_BF16, IN for PGF_EPI_BITMASK_BF16; col_partial: below.     */
 int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C,
                   long long ldc, int M, int N, int K, int epi, const float* bias, void* aux,
                   long long ld_aux, int stream_k, float* col_partial, void* stream);
 
 /* Fused bias gradient: with a bf16-output epilogue, col_partial (optional, fp32
- * [pgf_gemm_partial_rows(M)][N]) receives the column sums of the epilogue values of every 128-row
- * accumulator slab; pgf_reduce_partials() sums the slabs in a fixed order:
+ * [pgf_gemm_partial_rows(M)][N]) receives the column sums of the epilogue values of every 32-row
+ * accumulator slab (one per epilogue warp); pgf_reduce_partials() sums the slabs in a fixed order:
  *   out[n] = (coef ? coef[n] : 1) * sum_r partial[r][n]      (+= if accumulate)
  * replaces: the `.sum(0)` of autograd's nn.Linear bias gradient (fc_layers.0.bias).              */
 int pgf_gemm_partial_rows(int M);

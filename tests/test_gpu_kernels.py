@@ -353,10 +353,11 @@ def test_gemm_bf16_epilogues(dev):
     z = _gemm_ref(A, W, False, False)
     zb = z + bias.double().cpu()
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
-    for epi, ref in ((L.EPI_STORE_BF16, z), (L.EPI_BIAS_RELU_BF16, torch.relu(zb)), (L.EPI_BIAS_TANH_BF16, torch.tanh(zb)),
-                     (L.EPI_RELUMASK_BF16, z * (aux.cpu().double() > 0))):
-        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias, aux=aux if epi == L.EPI_RELUMASK_BF16 else None)
+    for epi, ref in ((L.EPI_STORE_BF16, z), (L.EPI_BIAS_RELU_BF16, torch.relu(zb)), (L.EPI_BIAS_TANH_BF16, torch.tanh(zb))):
+        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias)
         assert rel_err(out, ref) < 6e-3, (epi, rel_err(out, ref))   # bf16 output rounding: 2^-8
+    with pytest.raises(RuntimeError):                              # the bf16 mask-source epilogue was retired
+        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=L.EPI_RELUMASK_BF16)
     # ReLU sign bits: written by the forward epilogue (one uint32 per row x 32 columns), applied by the backward one
     bits = torch.full((M, N // 32), -1, dtype=torch.int32, device=dev)
     ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=L.EPI_BIAS_RELU_BF16, bias=bias, aux=bits)
@@ -398,25 +399,28 @@ def test_gemm_bf16_full_size_freivalds(dev):
     assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-4
 
 
-@pytest.mark.parametrize("M,N,K", [(520, 768, 512), (128, 264, 64), (1000, 2304, 768), (4096, 2560, 768)])
+@pytest.mark.parametrize("M,N,K", [(520, 768, 512), (128, 384, 64), (1000, 2304, 768), (4096, 2560, 768)])
 def test_gemm_fused_bias_gradient(dev, M, N, K):
-    """The ReLU-mask epilogue also reduces its fp32 values over the rows (db1 = colsum(dZ1)): per-128-row
+    """The sign-bit-mask epilogue also reduces its fp32 values over the rows (db1 = colsum(dZ1)): per-32-row
     slab partials inside the kernel, fixed-order sum outside -- no pass over the bf16 output."""
     from eeg_multimodal_b200 import _lib as L, ops
 
     g = torch.Generator().manual_seed(M + N)
     A = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
     W = (torch.randn(K, N, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)     # [K,N]: MN-major B, as dZ1 = dZ2 . W2
-    aux = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
-    ref = _gemm_ref(A, W, False, True) * (aux.cpu().double() > 0)
+    keep = torch.rand(M, N, generator=g) < 0.5
+    weights = (1 << torch.arange(32, dtype=torch.int64))
+    words = (keep.view(M, N // 32, 32).long() * weights).sum(-1)
+    bits = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).to(dev)
+    ref = _gemm_ref(A, W, False, True) * keep.double()
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     cs = torch.full((N,), float("nan"), device=dev)
-    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=aux, colsum_out=cs)
+    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits, colsum_out=cs)
     assert rel_err(out, ref) < 6e-3
     assert rel_err(cs, ref.sum(0)) < 2e-5, rel_err(cs, ref.sum(0))
     # deterministic: bit-identical on a second launch
     cs2 = torch.empty(N, device=dev)
-    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_RELUMASK_BF16, aux=aux, colsum_out=cs2)
+    ops.gemm_bf16(A, W, out, M=M, N=N, K=K, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits, colsum_out=cs2)
     assert torch.equal(cs, cs2)
 
 
@@ -503,3 +507,33 @@ def test_grouped_launch_with_per_model_seed_array(dev):
     # models 0 and 3 share a seed: identical noise, scaled by their own eps_hat
     n0 = (out[0] - out[3]).abs().max()
     assert float(n0) > 0 and not torch.equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_perturb_shared_batch_sweep_kernel_matches_single_model(dev, out_dtype):
+    """A large batch shared by the sweep goes through the shared-batch ring kernel (row fetched and normalised once,
+    perturbed once per model); every model's output is bit-identical to its own single-model launch."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    dims, M = (2048, 512), 3
+    D = sum(dims)
+    B = (1 << 22) // D + 61
+    g = torch.Generator(device=dev).manual_seed(8)
+    blocks = [torch.rand(B, d, device=dev, generator=g) for d in dims]
+    DP = torch.randn(M, D, device=dev, generator=g) * 0.2
+    w, eh, _ = ops.dp_coeffs(DP, torch.tensor([ho.exp_eps_f32(e) for e in (0.1, 1.0, 8.0)], device=dev))
+    seeds = [980616, 2 ** 63 + 5, 12]
+    sdev = torch.tensor([s if s < 2 ** 63 else s - 2 ** 64 for s in seeds], dtype=torch.int64, device=dev)
+    out, _, mn, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, model_seeds=sdev, offset=2, row0=B, n_models=M,
+                                         out_dtype=out_dtype, want_minmax=True)
+    it = torch.int16 if out_dtype == torch.bfloat16 else torch.int32
+    for m in range(M):
+        one, _, mn1, _ = ops.perturb_gate_fwd(blocks, w[m], eh[m], noise_mode=L.NOISE_PHILOX, seed=seeds[m], offset=2, row0=B,
+                                              out_dtype=out_dtype, want_minmax=True)
+        assert torch.equal(one.view(it), out[m].view(it))
+        assert torch.equal(mn1, mn[m])
+    # arithmetic-progression seeds (no device array) take the same kernel
+    out2, _, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=100, seed_step=7, offset=2, row0=B,
+                                         n_models=M, out_dtype=out_dtype)
+    one, _, _, _ = ops.perturb_gate_fwd(blocks, w[2], eh[2], noise_mode=L.NOISE_PHILOX, seed=114, offset=2, row0=B, out_dtype=out_dtype)
+    assert torch.equal(one.view(it), out2[2].view(it))
