@@ -3,7 +3,8 @@
 one JSON per report (duration, DRAM bytes, throughputs, occupancy, top stall reasons, hottest SASS lines)
 and profiles/ncu_traffic.json = measured DRAM bytes per launch keyed by the kernel names bench.py prints.
 
-    python tools/ncu_summary.py gpurun_out/r1_*.ncu-rep
+    python tools/ncu_summary.py [--outdir=DIR] gpurun_out/r1_*.ncu-rep
+(the reports are tens of MB each: run this on the GPU box and bring back only the summaries)
 """
 import csv
 import json
@@ -32,7 +33,8 @@ BENCH_NAMES = {
     "r1_gemm_dX_dDP_fused": ("gemm_bf16_tc M=65536 N=2560 K=2560 a_mn=0 b_mn=1 epi=8", 1),
     "r1_gemm_fwd2": ("gemm_bf16_tc M=65536 N=768 K=2560 a_mn=0 b_mn=0 epi=7", 1),
     "r1_gemm_dW1": ("gemm_bf16_tc M=2560 N=2560 K=65536 a_mn=1 b_mn=1 epi=4", 1),
-    "r1_perturb_fwd_philox_bf16": ("perturb_gate_fwd B=65536 D=2560 models=6 out=bf16", 6),
+    "r1_perturb_fwd_shared6_bf16": ("perturb_gate_fwd B=65536 D=2560 models=6 out=bf16", 1),
+    "r1_gemm_dW2": ("gemm_bf16_tc M=768 N=2560 K=65536 a_mn=1 b_mn=1 epi=4", 1),
     "r1_cls_ce_pass2": ("cls_ce B=65536 H=768 models=6 bwd=2", 6),
     "r1_cls_ce_pass1": ("cls_ce B=65536 H=768 models=6 bwd=1", 6),
 }
@@ -79,9 +81,10 @@ def summarise(rep):
 
 
 def main():
-    reps = sys.argv[1:]
-    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    reps = [a for a in sys.argv[1:] if not a.startswith("--outdir=")]
+    outdir = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--outdir=")), os.path.join(ROOT, "profiles"))
+    os.makedirs(outdir, exist_ok=True)
+    traffic_path = os.path.join(outdir, "ncu_traffic.json")
     try:
         traffic = json.load(open(traffic_path))
     except Exception:
@@ -90,7 +93,7 @@ def main():
         stem = os.path.splitext(os.path.basename(rep))[0]
         s = summarise(rep)
         json.dump({"report": os.path.basename(rep), "command": "ncu --set full --clock-control none --import-source on (tools/kbench.py --only <kernel> --iters 1)",
-                   "kernels": s}, open(os.path.join(ROOT, "profiles", stem + "_ncu.json"), "w"), indent=1)
+                   "kernels": s}, open(os.path.join(outdir, stem + "_ncu.json"), "w"), indent=1)
         m = s[0]["metrics"]
         rd, wr = m.get("dram__bytes_read.sum"), m.get("dram__bytes_write.sum")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
