@@ -103,8 +103,10 @@ class HeadEngine:
                 k = 1.0 / math.sqrt(shape[1])
                 self.view(wn)[i].copy_((torch.rand(shape, generator=g) * 2 - 1) * k)
                 self.view(bn)[i].copy_((torch.rand(shape[0], generator=g) * 2 - 1) * k)
-            if dp_init is not None:
-                self.DP[i].copy_(torch.as_tensor(dp_init, dtype=torch.float32).reshape(-1))
+            if dp_init is not None:   # one [D] vector for every model, or one per model ([M, D] / list of M vectors)
+                init = dp_init[i] if (isinstance(dp_init, (list, tuple)) or (torch.is_tensor(dp_init) and dp_init.dim() == 2
+                                                                             and dp_init.shape[0] == self.M and self.M > 1)) else dp_init
+                self.DP[i].copy_(torch.as_tensor(init, dtype=torch.float32).reshape(-1))
         self.sync_shadow()
 
     def sync_shadow(self):

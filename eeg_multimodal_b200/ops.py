@@ -347,15 +347,17 @@ def linear_adam_step(dY, X, W, mW, vW, bias, mb, vb, step, lr=1e-6, betas=(0.9, 
     for t, n in ((dY, "dY"), (X, "X"), (W, "W"), (mW, "mW"), (vW, "vW")):
         _chk(t, torch.float32, n)
     nm, sP = _grouped(W, 2)
+    if nm == 1:
+        sP = 0   # the stride of a size-1 dimension is meaningless (torch may report anything)
     B, N = dY.shape[-2:]
     K = X.shape[-1]
     assert W.shape[-2:] == (N, K) and W.stride(-2) == K, "W must be dense [N,K]"
     for t in (mW, vW):
-        assert t.shape == W.shape and t.stride() == W.stride()
+        assert t.shape == W.shape and (nm == 1 or t.stride() == W.stride())
     if bias is not None:
         for t in (bias, mb, vb):
             _chk(t, torch.float32, "bias")
-            assert (0 if t.dim() == 1 else t.stride(0)) == sP
+            assert nm == 1 or (0 if t.dim() == 1 else t.stride(0)) == sP
     _call(("linear_adam", B, N, K, nm), "pgf_linear_adam_step", dY.data_ptr(), dY.stride(-2), 0 if dY.dim() == 2 else dY.stride(0),
           X.data_ptr(), X.stride(-2), 0 if X.dim() == 2 else X.stride(0), B, N, K, W.data_ptr(), mW.data_ptr(), vW.data_ptr(),
           _ptr(bias), _ptr(mb), _ptr(vb), sP, int(step), float(lr), float(betas[0]), float(betas[1]), float(eps),

@@ -22,6 +22,7 @@ import sys
 import torch
 
 from . import parallel
+from . import variants as dp_variants
 from .engine import HeadEngine
 from .feature_cache import FeatureLoader, load_features, synthetic_features
 from .records import EpochMeter, RecordWriter, binary_f1
@@ -48,6 +49,8 @@ def build_parser():
     p.add_argument("--feature-dims", type=str, default="768,768,768")
     p.add_argument("--eps-list", type=str, default=None, help="comma list: train a sweep instead of one model")
     p.add_argument("--n-seeds", type=int, default=1)
+    p.add_argument("--variants", type=str, default=None,
+                   help="comma list of DP initialisation variants (zeros,newinit,tt,newinit_k1,newinit_k3,feawei): model_dict/newfrac_*")
     p.add_argument("--lr", type=float, default=1e-6)        # past_acc.py:157, train.py:75
     p.add_argument("--precision", choices=["fp32", "bf16"], default="fp32")
     p.add_argument("--unfixed-formula", action="store_true", help="eps_hat = log(..) as in model.py:57 (new_*eps runs)")
@@ -87,14 +90,20 @@ def run(cfg) -> dict:
     val_loader = FeatureLoader(vb, vl, cfg.batch_size, shuffle=True, seed=980616, device=dev)
 
     eps_list = [float(x) for x in cfg.eps_list.split(",")] if cfg.eps_list else [cfg.eps]
-    grid = parallel.sweep_grid(eps_list, cfg.n_seeds)
+    variants = [v.strip() or None for v in cfg.variants.split(",")] if cfg.variants else [None]
+    grid = parallel.sweep_grid(eps_list, cfg.n_seeds, variants=tuple(variants))
     mine = [grid[i] for i in parallel.shard_models(len(grid), world, rank)]
     if not mine:
         return {}
+    fmean = None
+    if any(v and (v.startswith("newinit_") or v == "feawei") for v in variants):
+        fmean = dp_variants.feature_mean(tb)                  # what the reference keeps in feawei.pkl
+    dp0 = [dp_variants.dp_init(g["variant"], dims, fmean) for g in mine]
     eng = HeadEngine(n_models=len(mine), feature_dims=dims, eps=[g["eps"] for g in mine], seeds=[g["seed"] for g in mine],
                      lr=cfg.lr, precision=cfg.precision, fixed_formula=not cfg.unfixed_formula,
-                     init_seed=980616, device=dev)
-    writers = [RecordWriter(cfg.records_root, f"newfrac_{g['eps']}eps_seed{g['seed']}/") for g in mine] if cfg.records_root else None
+                     init_seed=980616, device=dev, dp_init=dp0)
+    writers = [RecordWriter(cfg.records_root, f"newfrac_{g['eps']}eps" + (f"_{g['variant']}" if g["variant"] else "") + f"_seed{g['seed']}/")
+               for g in mine] if cfg.records_root else None
     want = [m.strip() for m in cfg.metrics.split(",")]
     results = {"Accuracy": [], "F1Score": [], "val_loss": [], "train_loss": []}
     best_acc = [0.0] * len(mine)

@@ -61,3 +61,90 @@ def test_train_driver_no_dp_pass_keeps_DP(tmp_path, monkeypatch):
         ["--synthetic", "64", "--feature-dims", "32,32", "--batch_size", "16", "--n_epochs", "1", "--n_eval", "1", "--n_dp", "0",
          "--eps", "1.0", "--lr", "1e-3"]))
     assert float(out["DP_params"].abs().max()) == 0.0
+
+
+def test_sweep_accuracy_matches_reference_within_seed_noise():
+    """North-star acceptance on a problem small enough for the CPU oracle: an eps sweep trained by the engine
+    (Philox noise, one grouped launch per kernel for all models) reaches the accuracy the reference's own
+    two-pass loop (torch RNG noise, oracle.TwoPassTrainer) reaches at each eps, within seed-to-seed spread, and
+    shows the reference's trend: accuracy collapses towards the majority rate as eps -> 0."""
+    from eeg_multimodal_b200 import HeadEngine
+    from oracle import head_oracle as ho
+
+    dev = torch.device("cuda:0")
+    dims, D, Bsz, epochs, lr = (64, 64, 64), 192, 8, 4, 2e-3
+    g = torch.Generator().manual_seed(11)
+
+    def make(n):
+        y = (torch.rand(n, generator=g) < 0.66).long()
+        blocks = []
+        for d in dims:
+            x = torch.rand(n, d, generator=g)
+            x[:, : d // 4] += y[:, None].float() * 0.35        # weakly separable: heavy noise destroys the signal
+            blocks.append(x)
+        return blocks, y
+
+    tr_b, tr_y = make(384)
+    va_b, va_y = make(256)
+    eps_list, n_seeds = [0.02, 1.0, 8.0], 3
+    p0 = ho.make_params(D, 768, seed=21)
+    sd = {"fc_layers.0.weight": p0.W1, "fc_layers.0.bias": p0.b1, "fc_layers.2.weight": p0.W2, "fc_layers.2.bias": p0.b2,
+          "classifier.weight": p0.Wc, "classifier.bias": p0.bc, "DP": p0.DP}
+
+    # ---- engine: the whole grid at once
+    grid = [(e, 100 + s) for e in eps_list for s in range(n_seeds)]
+    eng = HeadEngine(n_models=len(grid), feature_dims=dims, eps=[e for e, _ in grid], seeds=[s for _, s in grid], lr=lr, precision="fp32")
+    for i in range(len(grid)):
+        eng.load_state_dict(i, sd)
+    dtr, dty = [b.to(dev) for b in tr_b], tr_y.to(dev)
+    dva, dvy = [b.to(dev) for b in va_b], va_y.to(dev)
+    for ep in range(epochs):
+        for i in range(0, 384, Bsz):
+            eng.train_step([b[i:i + Bsz] for b in dtr], dty[i:i + Bsz])
+    acc_eng = torch.stack([eng.eval_step(dva, dvy)["acc"].cpu() for _ in range(3)]).mean(0).view(len(eps_list), n_seeds)
+
+    # ---- reference loop on the CPU (oracle), two seeds per eps
+    acc_ref = torch.zeros(len(eps_list), 2)
+    for ei, e in enumerate(eps_list):
+        for s in range(2):
+            t = ho.TwoPassTrainer(p0, e, lr=lr)
+            draw = 1000 * (ei + 1) + 50 * s
+            for ep in range(epochs):
+                for i in range(0, 384, Bsz):
+                    n1, g1 = ho.replay_reference_draws(draw, Bsz, D); draw += 1
+                    n2, g2 = ho.replay_reference_draws(draw, Bsz, D); draw += 1
+                    t.step([b[i:i + Bsz] for b in tr_b], tr_y[i:i + Bsz].view(-1, 1), n1, g1, n2, g2)
+            accs = []
+            for r in range(3):
+                nv, gv = ho.replay_reference_draws(draw, 256, D); draw += 1
+                with torch.no_grad():
+                    pred = ho.head_forward(va_b, t.p, e, nv, gv, True)
+                accs.append(float((pred.argmax(1) == va_y).float().mean()))
+            acc_ref[ei, s] = sum(accs) / len(accs)
+    me, mr = acc_eng.mean(1), acc_ref.mean(1)
+    print("engine acc per eps", me.tolist(), "reference acc per eps", mr.tolist())
+    assert float((me - mr).abs().max()) < 0.08, (me, mr)             # within seed noise at every eps
+    assert me[2] > 0.9 and mr[2] > 0.9                               # large budget: the problem is learnt
+    assert me[0] < me[2] - 0.1 and mr[0] < mr[2] - 0.1               # tiny budget: the noise drowns the signal
+
+
+def test_train_driver_init_variants(tmp_path, monkeypatch):
+    """--variants: the DP initialisations of model_dict/newfrac_1.0eps_{newinit,tt,newinit_k1}; the feature mean
+    ('feawei') comes from the normalise kernel and matches the oracle's min-max normalisation."""
+    from eeg_multimodal_b200 import feature_cache as fc, train, variants
+    from oracle import head_oracle as ho
+
+    monkeypatch.chdir(tmp_path)
+    tr = str(tmp_path / "train.npz")
+    _separable_cache(tr, 64, (64, 64, 64), 3)
+    blocks, _ = fc.load_features(tr)
+    fm = variants.feature_mean(blocks)
+    want = ho.minmax_normalise(torch.cat(blocks, 1)).mean(0)
+    assert float((fm - want).abs().max()) < 1e-6
+    out = train.run(train.build_parser().parse_args(
+        ["--batch_size", "8", "--n_epochs", "1", "--n_eval", "1", "--features", tr, "--eps", "1.0", "--variants", "newinit,tt,newinit_k1",
+         "--lr", "1e-6", "--n_dp", "0"]))
+    dp = out["DP_params"]
+    assert dp.shape == (3, 192)
+    assert torch.allclose(dp[0], variants.dp_init("newinit", (64, 64, 64))) and torch.allclose(dp[1], variants.dp_init("tt", (64, 64, 64)))
+    assert torch.allclose(dp[2], variants.dp_init("newinit_k1", (64, 64, 64), fm), atol=1e-6)

@@ -105,3 +105,29 @@ def test_sweep_grid_and_sharding():
         assert cuts[0][0] == 0 and cuts[-1][1] == gb
         assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
         assert max(hi - lo for lo, hi in cuts) - min(hi - lo for lo, hi in cuts) <= 1
+
+
+def test_dp_init_variants_follow_the_reference_formulas():
+    """past_acc.py:94-103: zeros / block constants (.4,.5,.3) / reversed / blocks + (1 - sigmoid(k*z)) - 0.5."""
+    from eeg_multimodal_b200 import variants
+
+    dims = (768, 768, 768)
+    assert torch.equal(variants.dp_init(None, dims), torch.zeros(2304))
+    ni = variants.dp_init("newinit", dims)
+    assert ni[0] == pytest.approx(0.4) and ni[768] == pytest.approx(0.5) and ni[-1] == pytest.approx(0.3)
+    assert torch.equal(variants.dp_init("tt", dims), torch.flip(ni, [0]))
+    rng = np.random.default_rng(0)
+    mean_values = rng.uniform(0.2, 0.8, 2304)
+    z = (mean_values - np.mean(mean_values)) / np.std(mean_values)
+    for name, k in (("newinit_1", 1.0), ("newinit_k1", 1.0), ("newinit_k3", 3.0), ("feawei", 1.0)):
+        w_init = 1 - torch.sigmoid(torch.tensor(k * z, dtype=torch.float32))          # the reference's expression
+        want = torch.cat((torch.full((1, 768), 0.4), torch.full((1, 768), 0.5), torch.full((1, 768), 0.3)), dim=1) + w_init.unsqueeze(0) - 0.5
+        assert torch.allclose(variants.dp_init(name, dims, mean_values), want.view(-1), atol=1e-7)
+    with pytest.raises(ValueError):
+        variants.dp_init("newinit_k1", dims)              # needs the feature mean
+    with pytest.raises(ValueError):
+        variants.dp_init("newinit", (2048, 512))          # block constants are defined for the 3-block layout
+    with pytest.raises(ValueError):
+        variants.dp_init("nonsense", dims)
+    grid = parallel.sweep_grid([1.0], n_seeds=2, variants=("newinit", "tt", None))
+    assert len(grid) == 6 and [g["variant"] for g in grid[:3]] == ["newinit", "tt", None]
