@@ -66,6 +66,7 @@ class HeadEngine:
             self.layout[name] = (off, shape)
             off += (n + 7) // 8 * 8  # 16-byte aligned segments in fp32 AND in the bf16 shadow (TMA)
         self.P = off
+        self._views = {}
         dev = self.device
         self.flat = torch.zeros(self.M, self.P, device=dev)
         self.grad = torch.zeros(self.M, self.P, device=dev)
@@ -89,9 +90,14 @@ class HeadEngine:
 
     # ---- parameters ----------------------------------------------------------------------------
     def view(self, name, src=None):
-        off, shape = self.layout[name]
+        """[M, *shape] view of one parameter inside a flat per-model buffer (views are cached: the buffers never move)."""
         src = self.flat if src is None else src
-        return src[:, off:off + math.prod(shape)].view(self.M, *shape)
+        key = (name, src.data_ptr())
+        v = self._views.get(key)
+        if v is None:
+            off, shape = self.layout[name]
+            v = self._views[key] = src[:, off:off + math.prod(shape)].view(self.M, *shape)
+        return v
 
     def _init_params(self, init_seed, dp_init):
         """nn.Linear default init (kaiming-uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))),
@@ -292,6 +298,10 @@ class HeadEngine:
         (shared by all models) or [M,B,Di]; labels int64 [B] / [B,1] (or [M,B]).
         `grad_hook(tensor)` is called on each gradient buffer before its Adam step (data-parallel
         all-reduce).  Returns per-model stats of pass 2: dict(loss[M], acc[M])."""
+        with ops.stream_scope():
+            return self._train_step(blocks, labels, row0, global_batch, grad_hook, dp_pass)
+
+    def _train_step(self, blocks, labels, row0, global_batch, grad_hook, dp_pass):
         labels = self._labels(labels)
         blocks = [b.contiguous() for b in blocks]
         if dp_pass:   # dp_pass=False reproduces train.py, where the DP pass is commented out (train.py:100-105)
@@ -315,6 +325,7 @@ class HeadEngine:
     def eval_step(self, blocks, labels, row0=0):
         """past_acc.py:218-228: hard=True, noise still sampled.  Returns dict(loss, acc, pred, logits)."""
         labels = self._labels(labels)
-        res = self._pass([b.contiguous() for b in blocks], labels, hard=True, mode="eval", row0=row0)
+        with ops.stream_scope():
+            res = self._pass([b.contiguous() for b in blocks], labels, hard=True, mode="eval", row0=row0)
         st = res["stats"].view(self.M, 4)
         return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], pred=res["pred"], logits=res["logits"])

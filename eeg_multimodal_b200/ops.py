@@ -7,8 +7,38 @@ import torch
 from . import _lib as L
 
 
+# torch.cuda.current_stream() costs more host time than the ctypes call it feeds; a caller that issues many
+# kernels back to back (HeadEngine) pins the handle for the duration of a step with `with ops.stream_scope():`
+_PINNED_STREAM = None
+
+
+class stream_scope:
+    def __enter__(self):
+        global _PINNED_STREAM
+        self.prev = _PINNED_STREAM
+        _PINNED_STREAM = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        global _PINNED_STREAM
+        _PINNED_STREAM = self.prev
+        return False
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _PINNED_STREAM if _PINNED_STREAM is not None else torch.cuda.current_stream().cuda_stream
+
+
+_QUERY_CACHE = {}
+
+
+def _query(name, *args) -> int:
+    """Workspace-size queries are pure functions of their arguments: cache them."""
+    key = (name, args)
+    v = _QUERY_CACHE.get(key)
+    if v is None:
+        v = _QUERY_CACHE[key] = L.query(name, *args)
+    return v
 
 
 def _ptr(t):
@@ -150,7 +180,7 @@ def perturb_gate_bwd_dp(dF, deps_dDP, *, noise_mode, lap=None, seed=0, offset=0,
     M = 1 if dF.dim() == 2 else dF.shape[0]
     if out is None:
         out = torch.empty((D,) if dF.dim() == 2 else (M, D), dtype=torch.float32, device=dF.device)
-    nbytes = L.query("pgf_perturb_gate_bwd_dp_workspace", B, D, M)
+    nbytes = _query("pgf_perturb_gate_bwd_dp_workspace", B, D, M)
     ws = workspace("perturb_bwd").get(nbytes, dF.device)
     s_dF = 0 if dF.dim() == 2 else dF.stride(0)
     s_coef = 0 if deps_dDP.dim() == 1 else deps_dDP.stride(0)
@@ -218,7 +248,7 @@ def linear_bwd_dx(dY, W, mask_src=None, mask_mode=L.ACT_RELU, out=None):
     if out is None:
         out = torch.empty((*dY.shape[:-1], K), dtype=torch.float32, device=dY.device)
     sdX = out.stride(0) if out.dim() == 3 else 0
-    nbytes = L.query("pgf_linear_bwd_dx_workspace", B, N, K, n_models)
+    nbytes = _query("pgf_linear_bwd_dx_workspace", B, N, K, n_models)
     ws = workspace("linear_dx").get(nbytes, dY.device)
     ld_mask = 0 if mask_src is None else mask_src.stride(-2)
     s_mask = 0 if mask_src is None or mask_src.dim() == 2 else mask_src.stride(0)
@@ -258,7 +288,7 @@ def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16,
         _chk(aux, torch.int32, "aux")   # packed ReLU sign bits
     part = None
     if colsum_out is not None:
-        rows = L.query("pgf_gemm_partial_rows", M)
+        rows = _query("pgf_gemm_partial_rows", M)
         part = workspace("gemm_partial").get(rows * N * 4, C.device)
     _call(("gemm", M, N, K, int(a_mn), int(b_mn), epi), "pgf_gemm_bf16", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(),
           B.stride(0), int(b_mn), C.data_ptr(), C.stride(0), M, N, K, epi, _ptr(bias), _ptr(aux),
@@ -274,7 +304,7 @@ def gemm_bf16_ddp(A, B, *, M, N, K, b_mn=True, seed, offset, row0, deps_dDP, out
     dL/dDP reduction fused into its epilogue (the [M,N] product is never written)."""
     _chk(A, torch.bfloat16, "A"); _chk(B, torch.bfloat16, "B")
     _chk(deps_dDP, torch.float32, "deps_dDP"); _chk(out, torch.float32, "dDP")
-    rows = L.query("pgf_gemm_partial_rows", M)
+    rows = _query("pgf_gemm_partial_rows", M)
     ws = workspace("gemm_partial").get(rows * N * 4, A.device)
     _call(("gemm", M, N, K, 0, int(b_mn), L.EPI_DDP_PARTIAL), "pgf_gemm_bf16_ddp", A.data_ptr(), A.stride(0), B.data_ptr(),
           B.stride(0), int(b_mn), M, N, K, int(seed), int(offset) & 0xFFFFFFFF, int(row0), deps_dDP.data_ptr(), ws.data_ptr(),
@@ -311,7 +341,7 @@ def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=
             dWc = torch.empty((*lead, 2, H), dtype=torch.float32, device=dev)
         if dbc is None and want_dw:
             dbc = torch.empty((*lead, 2), dtype=torch.float32, device=dev)
-    nbytes = L.query("pgf_cls_ce_workspace", B, H, n_models)
+    nbytes = _query("pgf_cls_ce_workspace", B, H, n_models)
     ws = workspace("cls_ce").get(nbytes, dev)
     g3 = lambda t: 0 if t is None or t.dim() < len(lead) + 1 or not lead else t.stride(0)
     _call(("cls_ce", B, H, n_models, _dt(h), (2 if (dWc is not None or dz_colsum is not None) else 1) if backward else 0), "pgf_cls_ce", h.data_ptr(), _dt(h), h.stride(-2), sh, Wc.data_ptr(), sWc, bc.data_ptr(), sbc, _ptr(labels), slab,
@@ -378,7 +408,7 @@ def colsum(x, out=None):
     B, N = x.shape
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=x.device)
-    nbytes = L.query("pgf_colsum_workspace", B, N)
+    nbytes = _query("pgf_colsum_workspace", B, N)
     ws = workspace("colsum").get(nbytes, x.device)
     _call(("colsum", B, N, _dt(x)), "pgf_colsum", x.data_ptr(), _dt(x), x.stride(0), B, N, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
     return out
