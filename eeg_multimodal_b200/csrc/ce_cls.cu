@@ -42,28 +42,73 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(void* p, long long off, const
 
 // MODE 0: forward only (eval).  MODE 1: + dz (pass 1 of the reference step: only the dX chain is
 // needed).  MODE 2: + dWc, dbc and the column sums of dz (= the bias gradient of fc_layers.2), pass 2.
-// Wc is staged in shared memory (6 KB) so the registers hold the row in flight and, in MODE 2, the
-// per-lane gradient accumulators; 2-3 CTAs of 8 warps per SM keep >= 48 KB of loads in flight per SM.
+// Each warp streams its rows through a private 3-stage ring of shared-memory row buffers filled by bulk async
+// copies (cp.async.bulk + mbarrier complete_tx, issued by lane 0 two rows ahead): register prefetching is
+// defeated by scoreboard aliasing (ncu: 25-35 % of the stall samples on the first FFMA of a row), and the ring
+// costs no registers, which MODE 2 needs for its gradient accumulators.  Wc is staged in shared memory.
 constexpr int CE_THREADS = 256;
+constexpr int CE_STAGES = 3;
+
+__device__ __forceinline__ uint32_t ce_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ce_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+template <typename T>
+__device__ __forceinline__ float4 lds4(const unsigned char* row, int j);
+template <>
+__device__ __forceinline__ float4 lds4<float>(const unsigned char* row, int j) {
+  return reinterpret_cast<const float4*>(row)[j];
+}
+template <>
+__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const unsigned char* row, int j) {
+  const uint2 u = reinterpret_cast<const uint2*>(row)[j];
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// dynamic shared memory: [Wc 2*H floats][ring: warps x CE_STAGES x row bytes, reused for the dWc combine][MODE 2: warps x H colsum]
+__host__ __device__ inline size_t ce_ring_bytes(int H, size_t esz, int mode) {
+  const size_t ring = static_cast<size_t>(CE_THREADS / 32) * CE_STAGES * H * esz;
+  const size_t comb = mode == 2 ? static_cast<size_t>(CE_THREADS / 32) * 2 * H * sizeof(float) : 0;
+  return ring > comb ? ring : comb;
+}
 
 template <int NV, typename HT, typename DT, int MODE>
 __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
   __shared__ float s_red[CE_THREADS / 32][4];
-  extern __shared__ float4 s_dyn4[];  // [2][H/4] Wc, then (MODE 2) [warps][3*H] floats of gradient partials
+  __shared__ __align__(8) unsigned long long s_full[CE_THREADS / 32][CE_STAGES];
+  extern __shared__ float4 s_dyn4[];
   const int model = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = CE_THREADS / 32;
   const int nvec = a.H >> 2;
   float4* s_w = s_dyn4;
+  unsigned char* s_ring = reinterpret_cast<unsigned char*>(s_dyn4 + 2 * nvec);
+  const uint32_t row_bytes = static_cast<uint32_t>(a.H) * static_cast<uint32_t>(sizeof(HT));
+  unsigned char* my_ring = s_ring + static_cast<size_t>(warp) * CE_STAGES * row_bytes;
+  float* s_cs = reinterpret_cast<float*>(s_ring + ce_ring_bytes(a.H, sizeof(HT), MODE));  // [warps][H] (MODE 2)
   {
     const float4* Wc = reinterpret_cast<const float4*>(a.Wc + model * a.sWc);
     for (int i = threadIdx.x; i < 2 * nvec; i += CE_THREADS) s_w[i] = Wc[i];
+    if (lane == 0) {
+#pragma unroll
+      for (int st = 0; st < CE_STAGES; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ce_smem_u32(&s_full[warp][st])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
   }
   // MODE 2 accumulators: dWc rows in registers, the dz column sums in the warp's own shared-memory row
-  // (keeping all three sets in registers spills inside the row loop at the 128-register budget of 2 CTAs/SM)
   float4 dw0[MODE == 2 ? NV : 1], dw1[MODE == 2 ? NV : 1];
-  float* s_dw = reinterpret_cast<float*>(s_dyn4 + 2 * nvec);  // [warps][3*H]: dWc row 0 | dWc row 1 | colsum(dz)
-  float* s_dsum = s_dw + warp * 3 * a.H + 2 * a.H;
+  float* s_dsum = s_cs + warp * a.H;
   if (MODE == 2) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -75,28 +120,39 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
   const float b0 = a.bc[model * a.sbc], b1 = a.bc[model * a.sbc + 1];
   const long long* labels = a.labels ? a.labels + model * a.slab : nullptr;  // NULL: logits/pred only
   float loss_sum = 0.f, correct = 0.f, db0 = 0.f, db1 = 0.f;
-  const long long hbase = model * a.sh, row_step = static_cast<long long>(gridDim.x) * nwarps;
+  const long long row_step = static_cast<long long>(gridDim.x) * nwarps;
+  const long long row_first = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const HT* hsrc = static_cast<const HT*>(a.h) + model * a.sh;
 
-  long long row = static_cast<long long>(blockIdx.x) * nwarps + warp;
-  float4 h[NV], hn[MODE == 2 ? 1 : NV];
-  if (row < a.B) {
+  auto issue = [&](int it) {  // lane 0: request row `it` of this warp
+    const long long r = row_first + static_cast<long long>(it) * row_step;
+    if (r >= a.B) return;
+    const int st = it % CE_STAGES;
+    const uint32_t bar = ce_smem_u32(&s_full[warp][st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ce_smem_u32(my_ring + static_cast<size_t>(st) * row_bytes)),
+                 "l"(hsrc + r * a.ldh), "r"(row_bytes), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int it = 0; it < CE_STAGES - 1; ++it) issue(it);
+  }
+
+  int it = 0;
+  for (long long row = row_first; row < a.B; row += row_step, ++it) {
+    const int st = it % CE_STAGES;
+    ce_mbar_wait(ce_smem_u32(&s_full[warp][st]), static_cast<uint32_t>(it / CE_STAGES) & 1u);
+    float4 h[NV];
+    const unsigned char* srow = my_ring + static_cast<size_t>(st) * row_bytes;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int col = (lane + 32 * k) << 2;
-      h[k] = col < a.H ? ld4<HT>(a.h, hbase + row * a.ldh + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int j = lane + 32 * k;
+      h[k] = (j << 2) < a.H ? lds4<HT>(srow, j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  }
-  for (; row < a.B; row += row_step) {
-    if (MODE != 2) {  // software prefetch of the warp's next row (two rows in flight per warp)
-      const long long nrow = row + row_step;
-      if (nrow < a.B) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int col = (lane + 32 * k) << 2;
-          hn[k] = col < a.H ? ld4<HT>(a.h, hbase + nrow * a.ldh + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
+    __syncwarp();                                  // every lane holds its part of the row: the previous stage is free
+    if (lane == 0) issue(it + CE_STAGES - 1);
     float z0 = 0.f, z1 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -159,19 +215,6 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
         }
       }
     }
-    if (MODE != 2) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) h[k] = hn[k];
-    } else {
-      const long long nrow = row + row_step;
-      if (nrow < a.B) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int col = (lane + 32 * k) << 2;
-          h[k] = col < a.H ? ld4<HT>(a.h, hbase + nrow * a.ldh + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
   }
   // ---- CTA-level combine, fixed order.  Partial row of a CTA: [4 scalars | dWc 2H | dz column sums H]
   const int pstride = 3 * a.H + 4;
@@ -182,17 +225,19 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     s_red[warp][2] = db0;
     s_red[warp][3] = db1;
   }
+  __syncthreads();  // every warp is done with its ring: the ring space now stages the per-warp dWc rows
+  float* s_dw = reinterpret_cast<float*>(s_ring);  // [warps][2*H]
   if (MODE == 2) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int col = (lane + 32 * k) << 2;
       if (col < a.H) {
-        *reinterpret_cast<float4*>(s_dw + warp * 3 * a.H + col) = dw0[k];
-        *reinterpret_cast<float4*>(s_dw + warp * 3 * a.H + a.H + col) = dw1[k];
+        *reinterpret_cast<float4*>(s_dw + warp * 2 * a.H + col) = dw0[k];
+        *reinterpret_cast<float4*>(s_dw + warp * 2 * a.H + a.H + col) = dw1[k];
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x < 4) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += s_red[w][threadIdx.x];
@@ -201,7 +246,11 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
   if (MODE == 2) {
     for (int i = threadIdx.x; i < 3 * a.H; i += CE_THREADS) {
       float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += s_dw[w * 3 * a.H + i];
+      if (i < 2 * a.H) {
+        for (int w = 0; w < nwarps; ++w) s += s_dw[w * 2 * a.H + i];
+      } else {
+        for (int w = 0; w < nwarps; ++w) s += s_cs[w * a.H + (i - 2 * a.H)];
+      }
       P[4 + i] = s;
     }
   }
@@ -268,8 +317,9 @@ size_t cls_ce_workspace(int B, int H, int n_models) {
 template <int NV>
 static int launch_ce(const CeArgs& a, int h_dtype, int dz_dtype, int mode, int n_models, int ctas, cudaStream_t s) {
   const dim3 grid(ctas, n_models), block(CE_THREADS);
-  const size_t smem = static_cast<size_t>(2) * a.H * sizeof(float) +
-                      (mode == 2 ? static_cast<size_t>(CE_THREADS / 32) * 3 * a.H * sizeof(float) : 0);
+  const size_t esz = h_dtype == PGF_DT_F32 ? 4 : 2;
+  const size_t smem = static_cast<size_t>(2) * a.H * sizeof(float) + ce_ring_bytes(a.H, esz, mode) +
+                      (mode == 2 ? static_cast<size_t>(CE_THREADS / 32) * a.H * sizeof(float) : 0);
 #define PGF_CE_LAUNCH(HT, DT, MD)                                                                        \
   do {                                                                                                   \
     if (smem > 32 * 1024)                                                                                \
@@ -303,6 +353,10 @@ int cls_ce(const CeArgs& a_in, int h_dtype, int dz_dtype, int bwd, int n_models,
   if (a.H % 4 != 0 || a.H > 1024) {
     set_error("pgf_cls_ce: hidden width H=%d must be a multiple of 4 and <= 1024", a.H);
     return PGF_ERR_UNSUPPORTED;
+  }
+  if (h_dtype != PGF_DT_F32 && ((a.H % 8) || (a.ldh % 8) || (a.sh % 8))) {
+    set_error("pgf_cls_ce: bf16 activations need H, ldh and the model stride to be multiples of 8 (16-byte bulk copies)");
+    return PGF_ERR_ARG;
   }
   if (workspace_bytes < cls_ce_workspace(a.B, a.H, n_models)) {
     set_error("pgf_cls_ce: workspace too small");
