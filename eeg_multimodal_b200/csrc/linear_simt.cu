@@ -48,35 +48,15 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinFwdArgs a) {
 #pragma unroll
   for (int r = 0; r < R; ++r) wrow[r] = reinterpret_cast<const float4*>(W + static_cast<long long>(min(n0 + r, a.N - 1)) * a.K);
 
-  constexpr int U = 2;  // k-steps in flight
-  int k = lane;
-  for (; k + 32 * (U - 1) < K4; k += 32 * U) {
-    float4 w[U][R];
+  // Two register sets of R weight vectors in ping-pong (written out by hand, no copies between them): the loads of
+  // k-step i+1 are issued before k-step i is consumed, and a set's scoreboard wait never covers the other set's loads.
+  auto load_w = [&](int k, float4 (&w)[R]) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int r = 0; r < R; ++r) w[u][r] = ldg_stream(wrow[r] + k + 32 * u);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int b = 0; b < TB; ++b) {
-        const float4 x = sx4[b * K4 + k + 32 * u];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          float s = acc[r * TB + b];
-          s = fmaf(x.x, w[u][r].x, s);
-          s = fmaf(x.y, w[u][r].y, s);
-          s = fmaf(x.z, w[u][r].z, s);
-          s = fmaf(x.w, w[u][r].w, s);
-          acc[r * TB + b] = s;
-        }
-      }
-    }
-  }
-  for (; k < K4; k += 32) {
-    float4 w[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) w[r] = ldg_stream(wrow[r] + k);
+    for (int r = 0; r < R; ++r)
+      if (k < K4) w[r] = ldg_stream(wrow[r] + k);
+  };
+  auto consume = [&](int k, const float4 (&w)[R]) {
+    if (k >= K4) return;
 #pragma unroll
     for (int b = 0; b < TB; ++b) {
       const float4 x = sx4[b * K4 + k];
@@ -90,6 +70,15 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinFwdArgs a) {
         acc[r * TB + b] = s;
       }
     }
+  };
+  float4 wA[R], wB[R];
+  int k = lane;
+  load_w(k, wA);
+  for (; k < K4; k += 64) {
+    load_w(k + 32, wB);
+    consume(k, wA);
+    load_w(k + 64, wA);
+    consume(k + 32, wB);
   }
   // warp reduction of R*TB values; every lane ends with the full sums
 #pragma unroll
