@@ -443,14 +443,12 @@ int linear_adam_step(const LinAdamArgs& a_in, int n_models, cudaStream_t s) {
   // of W / m / v instead of one long stream per CTA scattered over the whole 4 GB sweep state -- with 467-row slabs
   // the kernel ran at 73 % of HBM peak, with 32-row slabs at 85 % (fewer 2 MB pages live at once).
   static const int rows_exact = getenv("PGF_LINADAM_ROWS") ? atoi(getenv("PGF_LINADAM_ROWS")) : 0;
-  static const int unroll = getenv("PGF_LINADAM_U") ? atoi(getenv("PGF_LINADAM_U")) : 1;
   int rows = rows_exact > 0 ? rows_exact : 32;
   if (rows > a.N) rows = a.N;
   a.rows_per_cta = rows;
   const dim3 grid(kctas, (a.N + rows - 1) / rows, n_models);
   const size_t smem = static_cast<size_t>(rows) * TB * sizeof(float);
-  if (unroll >= 2) linear_adam_kernel<2><<<grid, 128, smem, s>>>(a);
-  else linear_adam_kernel<1><<<grid, 128, smem, s>>>(a);
+  linear_adam_kernel<1><<<grid, 128, smem, s>>>(a);  // two rows per register set spill at the 5-CTAs/SM register budget
   PGF_CUDA_LAUNCH_CHECK("pgf_linear_adam_step");
   return PGF_OK;
 }
