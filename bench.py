@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2048, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replay", choices=["auto", "on", "off"], default="auto",
+                    help="replay recorded C-ABI call plans instead of the Python wrappers (auto: the launch-bound workloads)")
     return ap.parse_args()
 
 
@@ -258,6 +260,8 @@ def run_ours(args):
     eng = HeadEngine(n_models=M, feature_dims=dims, hidden=HIDDEN, eps=eps, seeds=seeds, precision=precision,
                      init_seed=980616 + 1000 * (rank if args.workload != "dp64k" else 0))
 
+    eng.fast_replay = args.replay == "on" or (args.replay == "auto" and args.workload in ("sweep48_b8", "dp64k"))
+
     # ---- synthetic data resident in HBM (U(0,1) features, Bernoulli(0.66) labels)
     g = torch.Generator(device=dev).manual_seed(980616 + rank)
     nres = max(1, args.resident_batches)
@@ -375,7 +379,8 @@ def run_ours(args):
                 "config": {"workload": args.workload, "models_per_gpu": M, "models_total": total_models, "batch_per_model": B,
                            "feature_dims": list(dims), "hidden": HIDDEN, "eps": eps, "step": "reference two-pass step incl. both Adam updates",
                            "l2": f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)",
-                           "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce"},
+                           "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce",
+                           "host_path": "recorded call-plan replay" if eng.fast_replay else "python wrappers"},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
                 "loss_last": [float(x) for x in st["loss"].cpu()]}
         print(json.dumps(line))

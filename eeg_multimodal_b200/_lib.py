@@ -41,6 +41,7 @@ SIGNATURES = {
     "pgf_adam_step": (I, [P, P, P, P, P, LL, I, F, F, F, F, F, P]),
     "pgf_adam_step_strided": (I, [P, P, P, P, P, LL, LL, I, I, F, F, F, F, F, P]),
     "pgf_linear_adam_step": (I, [P, LL, LL, P, LL, LL, I, I, I, P, P, P, P, P, P, LL, I, F, F, F, F, F, I, P]),
+    "pgf_fill_zero": (I, [P, SZ, P]),
     "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
     "pgf_colsum_workspace": (SZ, [I, I]),
     "pgf_colsum": (I, [P, I, LL, I, I, P, P, SZ, P]),

@@ -1,5 +1,7 @@
 // extern "C" layer of libpgfuse.so: argument validation + dispatch to the kernels.
 // Contract: include/pgfuse.h.
+#include <map>
+#include <mutex>
 #include <stdarg.h>
 #include <string.h>
 
@@ -28,6 +30,48 @@ int num_sms() {
     cached_dev = dev;
   }
   return cached;
+}
+
+namespace {
+struct KernelKey {
+  int dev;
+  const void* k;
+  int threads;
+  size_t smem;
+  bool operator<(const KernelKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (k != o.k) return k < o.k;
+    if (threads != o.threads) return threads < o.threads;
+    return smem < o.smem;
+  }
+};
+std::mutex g_cache_mutex;
+std::map<KernelKey, size_t> g_smem_set;   // (dev, kernel) -> largest dynamic smem size configured so far
+std::map<KernelKey, int> g_occupancy;     // (dev, kernel, threads, smem) -> resident CTAs per SM
+}  // namespace
+
+void ensure_dynamic_smem(const void* kernel, size_t smem) {
+  if (smem <= 48 * 1024) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  size_t& cur = g_smem_set[KernelKey{dev, kernel, 0, 0}];
+  if (smem > cur) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cur = smem;
+  }
+}
+
+int cached_occupancy(const void* kernel, int threads, size_t smem, int fallback) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  auto it = g_occupancy.find(KernelKey{dev, kernel, threads, smem});
+  if (it != g_occupancy.end()) return it->second;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = fallback;
+  g_occupancy[KernelKey{dev, kernel, threads, smem}] = occ;
+  return occ;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -285,6 +329,13 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
   a.bias = bias; a.mb = mb; a.vb = vb; a.sP = sP; a.B = B; a.N = N; a.K = K; a.rows_per_cta = 0;
   a.c = make_adam_coef(step, lr, beta1, beta2, eps, grad_scale);
   return linear_adam_step(a, n_models, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_fill_zero(void* p, size_t nbytes, void* stream) {
+  if (nbytes == 0) return PGF_OK;
+  PGF_CHECK_ARG(p, "pgf_fill_zero: NULL pointer");
+  PGF_CUDA_CALL(cudaMemsetAsync(p, 0, nbytes, static_cast<cudaStream_t>(stream)));
+  return PGF_OK;
 }
 
 int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {

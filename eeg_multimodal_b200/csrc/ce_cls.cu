@@ -322,9 +322,7 @@ static int launch_ce(const CeArgs& a, int h_dtype, int dz_dtype, int mode, int n
                       (mode == 2 ? static_cast<size_t>(CE_THREADS / 32) * a.H * sizeof(float) : 0);
 #define PGF_CE_LAUNCH(HT, DT, MD)                                                                        \
   do {                                                                                                   \
-    if (smem > 32 * 1024)                                                                                \
-      cudaFuncSetAttribute(cls_ce_kernel<NV, HT, DT, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                           static_cast<int>(smem));                                                      \
+    ensure_dynamic_smem(reinterpret_cast<const void*>(cls_ce_kernel<NV, HT, DT, MD>), smem);              \
     cls_ce_kernel<NV, HT, DT, MD><<<grid, block, smem, s>>>(a);                                          \
   } while (0)
 #define PGF_CE_MODES(HT, DT)                         \

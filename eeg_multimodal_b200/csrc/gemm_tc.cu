@@ -708,8 +708,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
 #define PGF_GEMM_LAUNCH(AM, BMN, CGV)                                                                                     \
   do {                                                                                                                    \
     cfg.dynamicSmemBytes = Cfg<CGV>::SMEM_BYTES;                                                                          \
-    cudaFuncSetAttribute(gemm_bf16_tc_kernel<AM, BMN, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                  \
-                         Cfg<CGV>::SMEM_BYTES);                                                                           \
+    ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_bf16_tc_kernel<AM, BMN, CGV>), Cfg<CGV>::SMEM_BYTES);          \
     lerr = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<AM, BMN, CGV>, tmA, tmB, tmC, g);                                      \
   } while (0)
 #define PGF_GEMM_DISPATCH(CGV)                               \

@@ -111,11 +111,11 @@ int linear_fwd(const LinFwdArgs& a, int n_models, cudaStream_t s) {
   const long long ctas_r4 = static_cast<long long>((a.N + warps * 4 - 1) / (warps * 4)) * bchunks * n_models;
   const dim3 block(warps * 32);
   if (ctas_r4 >= 2LL * num_sms()) {
-    cudaFuncSetAttribute(linear_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dynamic_smem(reinterpret_cast<const void*>(linear_fwd_kernel<4>), smem);
     const dim3 grid((a.N + warps * 4 - 1) / (warps * 4), bchunks, n_models);
     linear_fwd_kernel<4><<<grid, block, smem, s>>>(a);
   } else {
-    cudaFuncSetAttribute(linear_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dynamic_smem(reinterpret_cast<const void*>(linear_fwd_kernel<2>), smem);
     const dim3 grid((a.N + warps * 2 - 1) / (warps * 2), bchunks, n_models);
     linear_fwd_kernel<2><<<grid, block, smem, s>>>(a);
   }
@@ -265,7 +265,7 @@ int linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float* W,
   const int bchunks = (B + TB - 1) / TB;
   const dim3 grid((K / 4 + 127) / 128, a.nslab, n_models * bchunks);
   const size_t smem = static_cast<size_t>(a.rows_per_slab) * TB * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(linear_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  ensure_dynamic_smem(reinterpret_cast<const void*>(linear_dx_kernel), smem);
   linear_dx_kernel<<<grid, 128, smem, s>>>(a);
   PGF_CUDA_LAUNCH_CHECK("pgf_linear_bwd_dx");
   const long long total = static_cast<long long>(B) * (K / 4);

@@ -482,9 +482,8 @@ static int launch_fwd_ring_shared(const PerturbFwdArgs& a, cudaStream_t stream) 
   constexpr int S = 3;
   const size_t smem = static_cast<size_t>(a.D) * sizeof(float) * S;
   auto kern = perturb_fwd_ring_shared_kernel<NV, OutT, S>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FWD_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+  const int occ = cached_occupancy(reinterpret_cast<const void*>(kern), FWD_THREADS, smem, 2);
   int gx = num_sms() * occ;
   if (gx > a.B) gx = a.B;
   kern<<<gx, FWD_THREADS, smem, stream>>>(a);
@@ -496,9 +495,8 @@ template <int NV, int NOISE, typename OutT, int RING_STAGES>
 static int launch_fwd_ring_s(const PerturbFwdArgs& a, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(a.D) * sizeof(float) * (RING_STAGES + (NOISE == PGF_NOISE_NONE ? 0 : 1));
   auto kern = perturb_fwd_ring_kernel<NV, NOISE, OutT, true, RING_STAGES>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FWD_THREADS, smem) != cudaSuccess || occ < 1) occ = 2;
+  ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+  const int occ = cached_occupancy(reinterpret_cast<const void*>(kern), FWD_THREADS, smem, 2);
   int gx = num_sms() * occ;
   if (gx > a.B) gx = a.B;
   kern<<<gx, FWD_THREADS, smem, stream>>>(a);
@@ -525,8 +523,7 @@ static int launch_fwd_ring_nv(const PerturbFwdArgs& a, int noise, int out_dtype,
 template <typename K>
 static int persistent_grid(K kernel, int threads, size_t smem, int n_models, int B) {
   // persistent CTAs: exactly one resident wave (SMs x occupancy), each CTA looping over rows
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 4;
+  const int occ = cached_occupancy(reinterpret_cast<const void*>(kernel), threads, smem, 4);
   int gx = (num_sms() * occ) / (n_models > 0 ? n_models : 1);
   if (gx > B) gx = B;
   if (gx < 1) gx = 1;

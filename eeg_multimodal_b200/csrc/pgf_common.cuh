@@ -54,6 +54,10 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+// Per-(device, kernel) caches of cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and of the occupancy query: both are
+// driver calls of several microseconds, which is a visible share of a launch in the launch-bound regimes.
+void ensure_dynamic_smem(const void* kernel, size_t smem);
+int cached_occupancy(const void* kernel, int threads, size_t smem, int fallback);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

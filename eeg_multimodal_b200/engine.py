@@ -80,6 +80,8 @@ class HeadEngine:
         self.t_model = 0
         self.t_dp = 0
         self.fuse_adam = True   # fp32 small-batch path: weight gradients recomputed inside the Adam kernel
+        self.fast_replay = False  # launch-bound regimes: replay recorded C-ABI call plans (see _train_step_planned)
+        self._plans = {}
         self.noise_offset = 0
         self._bufs = {}
         self._injected = None
@@ -145,10 +147,12 @@ class HeadEngine:
 
     # ---- helpers -------------------------------------------------------------------------------
     def _buf(self, name, shape, dtype):
-        t = self._bufs.get(name)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
-            self._bufs[name] = t
+        """Persistent scratch tensor per (name, shape, dtype): a differently-shaped batch (the tail of an epoch) gets
+        its own buffers instead of reallocating, so pointers held by recorded call plans stay valid."""
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.empty(shape, dtype=dtype, device=self.device)
         return t
 
     def inject_noise(self, lap, gum=None):
@@ -201,6 +205,15 @@ class HeadEngine:
             ops.perturb_gate_bwd_dp(dX, coef[2], noise_mode=L.NOISE_PHILOX, model_seeds=self.seeds_dev, offset=offset, row0=row0,
                                     out=self.dDP)
 
+    def _ce_out(self, mode, B):
+        """Persistent output buffers of the classifier/CE kernel (one set per pass kind, so the statistics of pass 2
+        survive the next step's pass 1 and recorded call plans see stable pointers).  Evaluation keeps fresh tensors."""
+        if mode == "eval":
+            return {}
+        M = self.M
+        return dict(logits=self._buf("logits_" + mode, (M, B, 2), torch.float32), pred=self._buf("pred_" + mode, (M, B), torch.int64),
+                    stats=self._buf("stats_" + mode, (M, 4), torch.float32))
+
     def _labels(self, labels):
         labels = labels.reshape(labels.shape[0], -1)[:, 0] if labels.dim() == 2 and labels.shape[-1] == 1 else labels
         return labels.contiguous()
@@ -221,7 +234,7 @@ class HeadEngine:
             coef, nspec = self._perturb(blocks, hard, X, row0)
             H1 = ops.linear_fwd(X, W1, b1, L.ACT_RELU, out=self._buf("H1", (M, B, D), torch.float32))
             H2 = ops.linear_fwd(H1, W2, b2, L.ACT_TANH, out=self._buf("H2", (M, B, H), torch.float32))
-            res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
+            res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward, **self._ce_out(mode, B),
                              dz=self._buf("dZ2", (M, B, H), torch.float32) if backward else None,
                              dWc=self.view("Wc", self.grad) if mode == "model" else None,
                              dbc=self.view("bc", self.grad) if mode == "model" else None, want_dw=mode == "model")
@@ -246,6 +259,8 @@ class HeadEngine:
             return res
         # ---- bf16 tensor-core path, one model at a time
         bf = torch.bfloat16
+        if mode == "model":   # the split-K weight-gradient GEMMs accumulate into a zeroed buffer
+            ops.fill_zero(self.grad)
         X = self._buf("Xh", (M, B, D), bf)
         coef, nspec = self._perturb(blocks, hard, X, row0)
         H1 = self._buf("H1h", (M, B, D), bf)
@@ -257,7 +272,7 @@ class HeadEngine:
             ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i],
                           aux=None if bits is None else bits[i])
             ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2[i])
-        res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
+        res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward, **self._ce_out(mode, B),
                          dz=self._buf("dZ2h", (M, B, H), bf) if backward else None, dz_dtype=bf,
                          dWc=self.view("Wc", self.grad) if mode == "model" else None,
                          dbc=self.view("bc", self.grad) if mode == "model" else None, want_dw=mode == "model",
@@ -285,7 +300,6 @@ class HeadEngine:
                     self._dDP_one(i, dX, coef, nspec, row0)
             return res
         gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
-        gW1.zero_(); gW2.zero_()
         for i in range(M):
             # dW = dZ^T . act: both operands are stored [K=B, *] -> MN-major, K = batch, split-K
             ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
@@ -299,7 +313,61 @@ class HeadEngine:
         `grad_hook(tensor)` is called on each gradient buffer before its Adam step (data-parallel
         all-reduce).  Returns per-model stats of pass 2: dict(loss[M], acc[M])."""
         with ops.stream_scope():
+            if self.fast_replay and self._injected is None:
+                return self._train_step_planned(blocks, labels, row0, global_batch, grad_hook, dp_pass)
             return self._train_step(blocks, labels, row0, global_batch, grad_hook, dp_pass)
+
+    def _state(self):
+        return (self.noise_offset, self.t_dp, self.t_model)
+
+    def _train_step_planned(self, blocks, labels, row0, global_batch, grad_hook, dp_pass):
+        """Launch-bound regimes: record the C-ABI calls of two steps with this input signature, then replay them
+        (ops.CallPlan) -- same functions, buffers and order, none of the Python between the launches."""
+        labels = self._labels(labels)
+        blocks = [b.contiguous() for b in blocks]
+        key = (tuple((tuple(b.shape), tuple(b.stride()), b.dtype) for b in blocks), tuple(labels.shape), tuple(labels.stride()),
+               global_batch, bool(dp_pass), grad_hook is not None)
+        ent = self._plans.get(key)
+        inputs = {("block", i): b.data_ptr() for i, b in enumerate(blocks)}
+        inputs["labels"] = labels.data_ptr()
+        if ent is not None and "plan" in ent:
+            n, rem = divmod(self.t_model - ent["state"][2], 1)
+            d = ent["dstate"]
+            ok = (self.noise_offset == ent["state"][0] + n * d[0] and self.t_dp == ent["state"][1] + n * d[1]
+                  and row0 == ent["row0"] + n * ent["drow0"])
+            if ok:
+                hook = None
+                if grad_hook is not None:
+                    hook = lambda which: grad_hook(self.dDP if which == "dDP" else self.grad)
+                ent["plan"].replay(n, inputs, hook)
+                self.noise_offset += d[0]
+                self.t_dp += d[1]
+                self.t_model += d[2]
+                return self._result(ent["stats"])
+            self._plans.pop(key)          # the step state no longer advances the way it did while recording
+            ent = None
+        # record this step through the ordinary wrapper path
+        state, rec = self._state(), []
+        ops.RECORD = rec
+        try:
+            result = self._train_step(blocks, labels, row0, global_batch, grad_hook, dp_pass)
+        finally:
+            ops.RECORD = None
+        ptrs = {v: k for k, v in inputs.items()}
+        if ent is None:
+            self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs)
+        else:
+            apart = state[2] - ent["state"][2]
+            try:
+                if apart < 1:
+                    raise RuntimeError("recorded steps out of order")
+                plan = ops.CallPlan(ent["rec"], rec, ent["ptrs"], ptrs, steps_apart=apart)
+                dstate = tuple((b - a) // apart for a, b in zip(ent["state"], state))
+                self._plans[key] = dict(plan=plan, state=ent["state"], dstate=dstate, row0=ent["row0"],
+                                        drow0=(row0 - ent["row0"]) // apart, stats=self._buf("stats_model", (self.M, 4), torch.float32))
+            except RuntimeError:
+                self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs)   # start over from this step
+        return result
 
     def _train_step(self, blocks, labels, row0, global_batch, grad_hook, dp_pass):
         labels = self._labels(labels)
@@ -307,6 +375,8 @@ class HeadEngine:
         if dp_pass:   # dp_pass=False reproduces train.py, where the DP pass is commented out (train.py:100-105)
             self._pass(blocks, labels, hard=False, mode="dp", row0=row0, global_batch=global_batch)
             if grad_hook is not None:
+                if ops.RECORD is not None:
+                    ops.RECORD.append((("hook",), None, ("dDP",)))
                 grad_hook(self.dDP)
             self.t_dp += 1
             ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
@@ -315,10 +385,17 @@ class HeadEngine:
                          fuse_adam=grad_hook is None and self.fuse_adam)
         if not res.get("adam_done"):
             if grad_hook is not None:
+                if ops.RECORD is not None:
+                    ops.RECORD.append((("hook",), None, ("grad",)))
                 grad_hook(self.grad)
             ops.adam_step(self.flat, self.grad, self.m, self.v, self.t_model, self.lr, self.betas, self.adam_eps,
                           bf16_shadow=self.shadow)
-        st = res["stats"].view(self.M, 4)
+        return self._result(res["stats"])
+
+    def _result(self, stats):
+        """Per-model statistics of pass 2 as fresh tensors (the kernels write into persistent buffers that the next
+        step overwrites)."""
+        st = stats.view(self.M, 4).clone()
         return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1])
 
     @torch.no_grad()

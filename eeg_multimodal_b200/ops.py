@@ -82,8 +82,15 @@ _ws = {}
 TIMING = None
 
 
+# when a list, every C-ABI call is appended as (tag, name, args): HeadEngine records two consecutive steps and turns
+# them into a CallPlan (below)
+RECORD = None
+
+
 def _call(tag, name, *args):
     """L.call, bracketed by CUDA events on the launching stream when bench.py asks for it."""
+    if RECORD is not None:
+        RECORD.append((tag, name, args))
     if TIMING is None:
         return L.call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -91,6 +98,73 @@ def _call(tag, name, *args):
     L.call(name, *args)
     e1.record()
     TIMING.append((tag, e0, e1))
+
+
+class CallPlan:
+    """The C-ABI calls of one engine step, replayable without the Python wrappers around them.
+
+    In the launch-bound regimes (few models per GPU at the reference batch size; small per-GPU shards of the
+    data-parallel mode) a step is ~20 kernels of a few microseconds each and the tensor-level wrappers (validation,
+    stride arithmetic, workspace look-ups) cost more host time than the GPU needs.  Two consecutive recorded steps
+    give, per call, the argument tuple and -- by difference -- the arguments that advance with the step (Philox
+    offsets, Adam step counts) and their increments; caller-supplied input pointers are substituted by position.
+    Replaying is then one ctypes call per kernel with the same C functions, same buffers, same order: results are
+    bit-identical to the wrapper path (tests/test_gpu_model.py)."""
+
+    def __init__(self, rec_a, rec_b, input_ptrs, input_ptrs_b=None, steps_apart=1):
+        """input_ptrs / input_ptrs_b: {data pointer: key} of the caller's input tensors in the two recorded steps."""
+        input_ptrs_b = input_ptrs if input_ptrs_b is None else input_ptrs_b
+        if len(rec_a) != len(rec_b) or any(a[1] != b[1] or len(a[2]) != len(b[2]) for a, b in zip(rec_a, rec_b)):
+            raise RuntimeError("the two recorded steps issued different call sequences")
+        lib = L.load()
+        self.calls = []
+        for (tag, name, a), (_, _, b) in zip(rec_a, rec_b):
+            if name is None:                      # marker: gradient hook (all-reduce) of the data-parallel mode
+                self.calls.append((tag, None, None, list(a), (), (), 0))
+                continue
+            types = L.SIGNATURES[name][1]
+            dyn, sub = [], []
+            for i, (x, y) in enumerate(zip(a, b)):
+                if types[i] is L.P:
+                    if x in input_ptrs:
+                        if input_ptrs_b.get(y) != input_ptrs[x]:
+                            raise RuntimeError(f"{name}: argument {i} is an input pointer in one recorded step but not in the other")
+                        sub.append((i, input_ptrs[x]))
+                    elif x != y:
+                        raise RuntimeError(f"{name}: pointer argument {i} changed between the recorded steps (buffers must be stable)")
+                elif x != y:
+                    if not (isinstance(x, int) and isinstance(y, int)) or (y - x) % steps_apart:
+                        raise RuntimeError(f"{name}: argument {i} changed between steps in a way a plan cannot replay ({x} -> {y})")
+                    dyn.append((i, (y - x) // steps_apart, 0xFFFFFFFF if types[i] is L.U32 else 0xFFFFFFFFFFFFFFFF))
+            self.calls.append((tag, name, getattr(lib, name), list(a), dyn, sub, L.LAUNCHES_PER_CALL.get(name, 1)))
+        self.n_launches = sum(c[6] for c in self.calls)
+
+    def replay(self, n, inputs, hook=None):
+        """Issue the step that lies n steps after the first recorded one; `inputs` maps the substitution keys to the
+        data pointers of this step's input tensors; `hook(which)` is called at the recorded gradient-hook points."""
+        lib = L.load()
+        for tag, name, fn, base, dyn, sub, _ in self.calls:
+            if name is None:
+                hook(base[0])
+                continue
+            args = base
+            if dyn or sub:
+                args = list(base)
+                for i, d, mask in dyn:
+                    args[i] = (base[i] + n * d) & mask
+                for i, key in sub:
+                    args[i] = inputs[key]
+            if TIMING is None:
+                rc = fn(*args)
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args)
+                e1.record()
+                TIMING.append((tag, e0, e1))
+            if rc != 0:
+                raise RuntimeError(f"{name} failed ({rc}): {lib.pgf_last_error().decode()}")
+        L.launch_count += self.n_launches
 
 
 def workspace(tag: str) -> Workspace:
@@ -127,7 +201,7 @@ def dp_coeffs(DP: torch.Tensor, exp_eps, fixed: bool = True, out=None):
     ee = _exp_eps_tensor(exp_eps, n_models, DP.device)
     if out is None:
         out = torch.empty(3, *DP.shape, dtype=torch.float32, device=DP.device)
-    L.call("pgf_dp_coeffs", DP.data_ptr(), ee.data_ptr(), int(fixed), D, n_models, out[0].data_ptr(), out[1].data_ptr(),
+    _call(("dp_coeffs", D, n_models), "pgf_dp_coeffs", DP.data_ptr(), ee.data_ptr(), int(fixed), D, n_models, out[0].data_ptr(), out[1].data_ptr(),
            out[2].data_ptr(), _stream())
     return out[0], out[1], out[2]
 
@@ -313,7 +387,7 @@ def gemm_bf16_ddp(A, B, *, M, N, K, b_mn=True, seed, offset, row0, deps_dDP, out
 
 
 def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=True, want_logits=True, want_pred=True,
-           dz_dtype=None, dz=None, dWc=None, dbc=None, want_dw=True, dz_colsum=None):
+           dz_dtype=None, dz=None, dWc=None, dbc=None, want_dw=True, dz_colsum=None, logits=None, pred=None, stats=None):
     """classifier + mean-CE + accuracy (+ backward).  Returns dict(logits, pred, stats, dz, dWc, dbc).
     want_dw=False (pass 1 of the reference step) forms dz only; dz_colsum [H] / [M,H] receives the
     column sums of dz (the bias gradient of fc_layers.2)."""
@@ -331,9 +405,12 @@ def cls_ce(h, Wc, bc, labels, *, loss_scale, grad_scale, backward, through_tanh=
     if labels is not None:
         _chk(labels, torch.int64, "labels")
         slab = labels.stride(0) if labels.dim() == 2 else 0
-    logits = torch.empty((*lead, B, 2), dtype=torch.float32, device=dev) if want_logits else None
-    pred = torch.empty((*lead, B), dtype=torch.int64, device=dev) if want_pred else None
-    stats = torch.empty((*lead, 4), dtype=torch.float32, device=dev)
+    if logits is None and want_logits:
+        logits = torch.empty((*lead, B, 2), dtype=torch.float32, device=dev)
+    if pred is None and want_pred:
+        pred = torch.empty((*lead, B), dtype=torch.int64, device=dev)
+    if stats is None:
+        stats = torch.empty((*lead, 4), dtype=torch.float32, device=dev)
     if backward:
         if dz is None:
             dz = torch.empty(h.shape, dtype=dz_dtype or h.dtype, device=dev)
@@ -394,12 +471,19 @@ def linear_adam_step(dY, X, W, mW, vW, bias, mb, vb, step, lr=1e-6, betas=(0.9, 
           float(grad_scale), nm, _stream())
 
 
+def fill_zero(t):
+    """cudaMemsetAsync on the current stream (a C-ABI call, so that it is part of recorded call plans)."""
+    _chk(t, None, "tensor")
+    assert t.is_contiguous()
+    _call(("fill_zero", t.numel() * t.element_size()), "pgf_fill_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())
+
+
 def cast_bf16(src, dst=None):
     _chk(src, torch.float32, "src")
     assert src.is_contiguous()
     if dst is None:
         dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    L.call("pgf_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+    _call(("cast_bf16", src.numel()), "pgf_cast_f32_to_bf16", src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
     return dst
 
 

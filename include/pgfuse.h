@@ -200,6 +200,8 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
 
 /* ---- helpers for the tensor-core path ---------------------------------------------------------*/
 int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* zero-fill (the split-K weight-gradient GEMMs accumulate into a zeroed buffer; replaces grad.zero_()) */
+int pgf_fill_zero(void* p, size_t nbytes, void* stream);
 size_t pgf_colsum_workspace(int B, int N);
 int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out, float* workspace,
                size_t workspace_bytes, void* stream);

@@ -272,3 +272,40 @@ def test_engine_fused_gradient_adam_is_bit_identical(dev):
     assert torch.equal(a.flat, b.flat) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v)
     assert torch.equal(a.DP, b.DP) and torch.equal(sa["loss"], sb["loss"])
     assert not torch.equal(a.flat[0], a.flat[1])
+
+
+@pytest.mark.parametrize("precision,dims,B", [("fp32", (768, 768, 768), 8), ("bf16", (2048, 512), 512)])
+def test_call_plan_replay_is_bit_identical(dev, precision, dims, B):
+    """Launch-bound regimes replay recorded C-ABI call plans instead of going through the Python wrappers: same
+    functions, buffers and order, so parameters, moments, DP and the returned statistics are bit-identical -- with
+    input tensors that move every step, a differently-shaped tail batch in between, and a gradient hook."""
+    from eeg_multimodal_b200 import HeadEngine
+
+    M = 2
+    g = torch.Generator().manual_seed(3)
+    batches = [([torch.rand(B, d, generator=g).to(dev) for d in dims], (torch.rand(B, generator=g) < 0.66).long().to(dev)) for _ in range(3)]
+    tail = ([torch.rand(B // 2, d, generator=g).to(dev) for d in dims], (torch.rand(B // 2, generator=g) < 0.66).long().to(dev))
+    order = [0, 1, 2, 0, "tail", 1, 2, 0, 1]
+    hooked = []
+
+    def run(replay, hook):
+        e = HeadEngine(n_models=M, feature_dims=dims, eps=[0.5, 4.0], seeds=[11, 980616], lr=1e-3, precision=precision)
+        e.fast_replay = replay
+        losses = []
+        for i, k in enumerate(order):
+            blocks, labels = tail if k == "tail" else batches[k]
+            st = e.train_step(blocks, labels, row0=i * B, grad_hook=hook)
+            losses.append(st["loss"].clone())
+        return e, torch.stack(losses)
+
+    for use_hook in (False, True):
+        hook = (lambda t: hooked.append(t.data_ptr())) if use_hook else None
+        hooked.clear()
+        a, la = run(False, hook)
+        n_slow = len(hooked)
+        b, lb = run(True, hook)
+        assert torch.equal(la, lb)
+        assert torch.equal(a.flat, b.flat) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v) and torch.equal(a.DP, b.DP)
+        assert b._plans and any("plan" in v for v in b._plans.values())          # the plan was built and used
+        if use_hook:
+            assert len(hooked) == 2 * n_slow and n_slow == 2 * len(order)          # dDP + grad hook on every step, both runs
