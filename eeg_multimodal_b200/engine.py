@@ -334,7 +334,7 @@ class HeadEngine:
             n, rem = divmod(self.t_model - ent["state"][2], 1)
             d = ent["dstate"]
             ok = (self.noise_offset == ent["state"][0] + n * d[0] and self.t_dp == ent["state"][1] + n * d[1]
-                  and row0 == ent["row0"] + n * ent["drow0"])
+                  and row0 == ent["row0"] + n * ent["drow0"] and ent["plan"].ws_generation == ops.WS_GENERATION)
             if ok:
                 hook = None
                 if grad_hook is not None:

@@ -63,6 +63,9 @@ def _chk(t, dtype=None, name="tensor"):
     return t
 
 
+WS_GENERATION = 0   # bumped whenever a scratch buffer is (re)allocated: recorded call plans hold raw pointers into them
+
+
 class Workspace:
     """Grow-only scratch buffer (caller-owned scratch of the C ABI)."""
 
@@ -70,9 +73,11 @@ class Workspace:
         self.buf = None
 
     def get(self, nbytes: int, device) -> torch.Tensor:
+        global WS_GENERATION
         n = max(4, (nbytes + 3) // 4)
         if self.buf is None or self.buf.numel() < n or self.buf.device != device:
             self.buf = torch.empty(n, dtype=torch.float32, device=device)
+            WS_GENERATION += 1
         return self.buf
 
 
@@ -138,6 +143,7 @@ class CallPlan:
                     dyn.append((i, (y - x) // steps_apart, 0xFFFFFFFF if types[i] is L.U32 else 0xFFFFFFFFFFFFFFFF))
             self.calls.append((tag, name, getattr(lib, name), list(a), dyn, sub, L.LAUNCHES_PER_CALL.get(name, 1)))
         self.n_launches = sum(c[6] for c in self.calls)
+        self.ws_generation = WS_GENERATION   # the plan is void once any scratch buffer it may point into has moved
 
     def replay(self, n, inputs, hook=None):
         """Issue the step that lies n steps after the first recorded one; `inputs` maps the substitution keys to the
