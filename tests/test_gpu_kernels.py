@@ -373,6 +373,15 @@ def test_gemm_bf16_epilogues(dev):
     o32 = torch.empty(M, N, device=dev)
     ops.gemm_bf16(A, W, o32, M=M, N=N, K=K, epi=L.EPI_BIAS_F32, bias=bias)
     assert rel_err(o32, zb) < 1e-5
+    # fused tanh (MUFU.EX2 + MUFU.RCP form): absolute error at the fp32 rounding level, exact saturation
+    big = bias.clone()
+    big[:8] = 30.0
+    big[8:16] = -30.0
+    big[16:24] = 1e-4
+    ops.gemm_bf16(A, W, o32, M=M, N=N, K=K, epi=L.EPI_BIAS_TANH_F32, bias=big)
+    want = torch.tanh(z + big.double().cpu())
+    assert float((o32.cpu().double() - want).abs().max()) < 5e-6   # incl. the fp32 accumulation error of z itself
+    assert bool((o32[:, :8] == 1.0).all()) and bool((o32[:, 8:16] == -1.0).all())
 
 
 def test_gemm_bf16_full_size_freivalds(dev):
