@@ -151,6 +151,12 @@ def kernel_work(tag):
     if kind == "linear_adam":   # read + write of W and both moments; the gradient is recomputed, never stored
         _, b, n, k, m = tag
         return f"linear_adam B={b} N={n} K={k} models={m}", "hbm", float(m) * n * k * 24
+    if kind == "fill_zero":
+        return f"fill_zero bytes={tag[1]}", "hbm", float(tag[1])
+    if kind == "dp_coeffs":
+        return f"dp_coeffs D={tag[1]} models={tag[2]}", "hbm", float(tag[1]) * tag[2] * 16
+    if kind == "cast_bf16":
+        return f"cast_bf16 n={tag[1]}", "hbm", float(tag[1]) * 6
     if kind == "reduce_partials":
         return f"reduce_partials rows={tag[1]} N={tag[2]}", "hbm", float(tag[1]) * tag[2] * 4
     if kind in ("linear_fwd", "linear_bwd_dx", "linear_bwd_dw"):
