@@ -546,3 +546,78 @@ def test_perturb_shared_batch_sweep_kernel_matches_single_model(dev, out_dtype):
                                          n_models=M, out_dtype=out_dtype)
     one, _, _, _ = ops.perturb_gate_fwd(blocks, w[2], eh[2], noise_mode=L.NOISE_PHILOX, seed=114, offset=2, row0=B, out_dtype=out_dtype)
     assert torch.equal(one.view(it), out2[2].view(it))
+
+
+def _guarded(shape, dtype, dev, fill):
+    """A tensor of `shape` carved out of the middle of a larger sentinel-filled allocation; returns (view, check)."""
+    n = int(np.prod(shape))
+    pad = 4096
+    big = torch.full((n + 2 * pad,), fill, dtype=dtype, device=dev)
+    view = big[pad:pad + n].view(*shape)
+
+    def check():
+        lo, hi = big[:pad], big[pad + n:]
+        ok = (lo == fill) & (hi == fill) if fill == fill else (torch.isnan(lo.float()) & torch.isnan(hi.float()))
+        assert bool(ok.all()), "out-of-bounds write next to a kernel output"
+    return view, check
+
+
+def test_no_out_of_bounds_writes_at_ragged_sizes(dev):
+    """compute-sanitizer is not available on the GPU pool: every kernel family writes into outputs carved out of
+    sentinel-filled allocations at sizes that are not multiples of its tiles, and the guard zones must survive."""
+    from eeg_multimodal_b200 import _lib as L, ops
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    checks = []
+
+    def G(shape, dtype=torch.float32, fill=float("nan")):
+        v, c = _guarded(shape, dtype, dev, fill)
+        checks.append(c)
+        return v
+
+    # tcgen05 GEMM: M, N not multiples of the 128/256 tiles; fp32 store, bf16 + sign bits, mask + column partials, dDP
+    M, N, K = 200, 384, 136
+    A = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
+    W = torch.randn(N, K, device=dev, generator=g).to(torch.bfloat16)
+    Wt = torch.randn(K, N, device=dev, generator=g).to(torch.bfloat16)
+    ops.gemm_bf16(A, W, G((M, N)), M=M, N=N, K=K, epi=L.EPI_STORE_F32)
+    bits = G((M, N // 32), torch.int32, fill=-7)
+    ops.gemm_bf16(A, W, G((M, N), torch.bfloat16), M=M, N=N, K=K, epi=L.EPI_BIAS_RELU_BF16, bias=torch.zeros(N, device=dev), aux=bits)
+    ops.gemm_bf16(A, Wt, G((M, N), torch.bfloat16), M=M, N=N, K=K, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=bits, colsum_out=G((N,)))
+    ops.gemm_bf16_ddp(A, Wt, M=M, N=N, K=K, b_mn=True, seed=3, offset=1, row0=5, deps_dDP=torch.ones(N, device=dev), out=G((N,)))
+    Cs = G((N, 264), fill=0.0)
+    ops.gemm_bf16(Wt, torch.randn(K, 264, device=dev, generator=g).to(torch.bfloat16), Cs, M=N, N=264, K=K, a_mn=True, b_mn=True,
+                  epi=L.EPI_ATOMIC_F32, stream_k=True)
+    # perturb: generic (small), TMA ring (large), shared-batch sweep ring
+    dims = (772, 128, 64)
+    D = sum(dims)
+    for B, nm in ((3, 1), ((1 << 22) // D + 5, 1), ((1 << 22) // D + 5, 2)):
+        blocks = [torch.rand(B, d, device=dev, generator=g) for d in dims]
+        w, eh, _ = ops.dp_coeffs(torch.zeros(nm, D, device=dev) if nm > 1 else torch.zeros(D, device=dev), [2.7] * nm if nm > 1 else 2.7)
+        for dt in (torch.float32, torch.bfloat16):
+            ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=1, n_models=nm,
+                                 out=G((nm, B, D) if nm > 1 else (B, D), dt))
+    # classifier + CE: ragged batch, bf16 and fp32 activations, all modes
+    B, H = 33, 264
+    h = torch.tanh(torch.randn(2, B, H, device=dev, generator=g))
+    Wc, bc = torch.randn(2, 2, H, device=dev, generator=g), torch.zeros(2, 2, device=dev)
+    lab = (torch.rand(B, device=dev, generator=g) < 0.5).long()
+    ops.cls_ce(h, Wc, bc, lab, loss_scale=1.0, grad_scale=1.0, backward=True, dz=G((2, B, H)), dWc=G((2, 2, H)), dbc=G((2, 2)),
+               dz_colsum=G((2, H)), logits=G((2, B, 2)), pred=G((2, B), torch.int64, fill=-1), stats=G((2, 4)))
+    ops.cls_ce(h.to(torch.bfloat16), Wc, bc, lab, loss_scale=1.0, grad_scale=1.0, backward=True, want_dw=False,
+               dz=G((2, B, H), torch.bfloat16), logits=G((2, B, 2)), pred=G((2, B), torch.int64, fill=-1), stats=G((2, 4)))
+    # grouped fp32 linear kernels and the fused gradient+Adam at sizes off every tile
+    Mo, Bq, Nn, Kk = 3, 5, 100, 132
+    X = torch.randn(Mo, Bq, Kk, device=dev, generator=g)
+    Wl = G((Mo, Nn, Kk), fill=0.5)
+    bl = torch.zeros(Mo, Nn, device=dev)
+    ops.linear_fwd(X, Wl, bl, L.ACT_TANH, out=G((Mo, Bq, Nn)))
+    dY = torch.randn(Mo, Bq, Nn, device=dev, generator=g)
+    ops.linear_bwd_dx(dY, Wl, out=G((Mo, Bq, Kk)))
+    ops.linear_bwd_dw(dY, X, dW=G((Mo, Nn, Kk)), db=G((Mo, Nn)))
+    mW, vW = G((Mo, Nn, Kk), fill=0.0), G((Mo, Nn, Kk), fill=0.0)
+    ops.linear_adam_step(dY, X, Wl, mW, vW, None, None, None, step=1, lr=1e-3)
+    ops.adam_step(G((1001,), fill=1.0), torch.ones(1001, device=dev), G((1001,), fill=0.0), G((1001,), fill=0.0), 1)
+    torch.cuda.synchronize()
+    for c in checks:
+        c()
