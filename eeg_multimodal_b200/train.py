@@ -165,7 +165,13 @@ def run(cfg) -> dict:
 
 
 def main(argv=None):
-    run(build_parser().parse_args(argv))
+    import torch.distributed as dist
+
+    try:
+        run(build_parser().parse_args(argv))
+    finally:
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
