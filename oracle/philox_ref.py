@@ -8,7 +8,7 @@ which are sequential and device-specific.  The product path replaces them by Phi
 every (sample row, column, pass) has its own counter: noise is independent of batch
 partitioning and of the GPU count.  This file defines that mapping bit-for-bit; the CUDA
 side (`csrc/philox.cuh`) must produce the same uint32 words, checked in
-`tests/test_perturb_gate.py`.
+`tests/test_gpu_kernels.py::test_perturb_gate_philox_matches_oracle_noise`.
 
 Counter / key layout (one Philox call yields the four words of four consecutive columns):
     counter = (col // 4, row_global, stream, offset)      key = (seed_lo, seed_hi)
