@@ -44,8 +44,8 @@ def sweep_main(a):
     W2, b2 = flat[:, o2:o2 + H * D].view(M, H, D), flat[:, o2 + H * D:o2 + H * D + H]
     mv = lambda t, off, shape: t[:, off:off + shape[0] * (shape[1] if len(shape) > 1 else 1)].view(M, *shape)
     X = torch.rand(M, B, D, device=dev)
-    H1 = torch.rand(M, B, D, device=dev)
-    dZ1 = torch.randn(M, B, D, device=dev) * 1e-3
+    H1 = torch.relu(torch.randn(M, B, D, device=dev))          # ReLU output: half of the entries are exactly zero
+    dZ1 = torch.randn(M, B, D, device=dev) * 1e-3 * (torch.rand(M, B, D, device=dev) < 0.5)
     dZ2 = torch.randn(M, B, H, device=dev) * 1e-3
     Y1, Y2, dX = torch.empty(M, B, D, device=dev), torch.empty(M, B, H, device=dev), torch.empty(M, B, D, device=dev)
     cases = [
