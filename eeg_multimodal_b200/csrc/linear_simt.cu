@@ -33,14 +33,22 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinFwdArgs a) {
   const int K4 = a.K >> 2;
   const float* X = a.X + model * a.sX + static_cast<long long>(b0) * a.ldx;
   const float* W = a.W + model * a.sW;
+  // Activation tile -> shared memory with 16-byte async copies (LDGSTS: no register staging, all of a thread's copies
+  // in flight at once); the first weight vectors are requested BEFORE the wait, so the weight stream is already running
+  // while the tile lands (ncu: the LDG->STS staging loop held 23 % of this kernel's stall samples).
   for (int i = threadIdx.x; i < TB * K4; i += blockDim.x) {
     const int b = i / K4, k = i - b * K4;
-    sx4[i] = b < nb ? *reinterpret_cast<const float4*>(X + b * a.ldx + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < nb) {
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(sx4 + i));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(X + b * a.ldx + 4 * k) : "memory");
+    } else {
+      sx4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  __syncthreads();
+  asm volatile("cp.async.commit_group;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * R;
-  if (n0 >= a.N) return;
+  const bool active = n0 < a.N;
   float acc[R * TB];
 #pragma unroll
   for (int i = 0; i < R * TB; ++i) acc[i] = 0.f;
@@ -73,7 +81,10 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const LinFwdArgs a) {
   };
   float4 wA[R], wB[R];
   int k = lane;
-  load_w(k, wA);
+  if (active) load_w(k, wA);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (!active) return;
   for (; k < K4; k += 64) {
     load_w(k + 32, wB);
     consume(k, wA);
