@@ -133,8 +133,10 @@ def kernel_work(tag):
         _, m, n, k, a_mn, b_mn, epi = tag
         return f"gemm_bf16_tc M={m} N={n} K={k} a_mn={a_mn} b_mn={b_mn} epi={epi}", "tensor", 2.0 * m * n * k
     if kind == "perturb_fwd":
-        _, b, d, m, dt, noise, gate = tag
-        return f"perturb_gate_fwd B={b} D={d} models={m} out={'f32' if dt == 0 else 'bf16'}", "hbm", float(m) * b * d * (4 + (4 if dt == 0 else 2))
+        _, b, d, m, dt, noise, gate, shared = tag
+        osz = 4 if dt == 0 else 2   # a batch shared by the sweep is read once, every model writes its own perturbed copy
+        nbytes = float(b) * d * (4 + m * osz) if shared else float(m) * b * d * (4 + osz)
+        return f"perturb_gate_fwd B={b} D={d} models={m} out={'f32' if dt == 0 else 'bf16'}", "hbm", nbytes
     if kind == "perturb_bwd_dp":
         _, b, d, m, dt = tag
         return f"perturb_bwd_dp B={b} D={d} models={m}", "hbm", float(m) * b * d * (4 if dt == 0 else 2)

@@ -464,13 +464,36 @@ __global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_shared_kernel
       v[k].w = __fmul_rn(__fsub_rn(v[k].w, mn), inv_range);
     }
     const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+    // Models that share a seed draw the SAME noise by definition (same Philox key and counters) -- an eps sweep at one
+    // seed, which is how the sweep grid lands on a GPU: the log2-uniforms with the Laplace sign folded in are computed
+    // once per run of equal seeds and every model of the run only scales them by its own eps_hat row (one FMA per
+    // element).  (lg2 ^ sign) * c == lg2 * (c ^ sign) bit for bit, so the result equals the single-model kernel's.
+    float4 sl[NV];
+    unsigned int have_lo = 0u, have_hi = 0u;
+    bool have = false;
 #pragma unroll 1
     for (int m = 0; m < a.n_models; ++m) {
-      PhiloxKeys rk;
+      const uint4 kq0 = s_rk[5 * m];
+      if (!have || kq0.x != have_lo || kq0.y != have_hi) {   // first round key pair == the seed
+        PhiloxKeys rk;
+        rk.k[0] = kq0.x; rk.k[1] = kq0.y; rk.k[2] = kq0.z; rk.k[3] = kq0.w;
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const uint4 kq = s_rk[5 * m + q];
-        rk.k[4 * q] = kq.x; rk.k[4 * q + 1] = kq.y; rk.k[4 * q + 2] = kq.z; rk.k[4 * q + 3] = kq.w;
+        for (int q = 1; q < 5; ++q) {
+          const uint4 kq = s_rk[5 * m + q];
+          rk.k[4 * q] = kq.x; rk.k[4 * q + 1] = kq.y; rk.k[4 * q + 2] = kq.z; rk.k[4 * q + 3] = kq.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int j = tid + FWD_THREADS * k;
+          if (j < nvec) {
+            const uint4 r = philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, rk);
+            sl[k] = make_float4(signed_lg2_from_bits(r.x), signed_lg2_from_bits(r.y), signed_lg2_from_bits(r.z),
+                                signed_lg2_from_bits(r.w));
+          }
+        }
+        have = true;
+        have_lo = kq0.x;
+        have_hi = kq0.y;
       }
       const float4* ge = reinterpret_cast<const float4*>(a.eps_hat + m * a.s_coef);
       char* outp = static_cast<char*>(a.out) + m * a.s_out * static_cast<long long>(sizeof(OutT));
@@ -483,12 +506,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 5) perturb_fwd_ring_shared_kernel
         const int j = tid + FWD_THREADS * k;
         if (j < nvec) {
           const float4 e4 = __ldg(ge + j);
-          const uint4 r = philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, rk);
           float4 o;
-          o.x = perturb_fma(v[k].x, r.x, __fmul_rn(e4.x, -0.69314718055994531f));
-          o.y = perturb_fma(v[k].y, r.y, __fmul_rn(e4.y, -0.69314718055994531f));
-          o.z = perturb_fma(v[k].z, r.z, __fmul_rn(e4.z, -0.69314718055994531f));
-          o.w = perturb_fma(v[k].w, r.w, __fmul_rn(e4.w, -0.69314718055994531f));
+          o.x = __fmaf_rn(sl[k].x, __fmul_rn(e4.x, -0.69314718055994531f), v[k].x);
+          o.y = __fmaf_rn(sl[k].y, __fmul_rn(e4.y, -0.69314718055994531f), v[k].y);
+          o.z = __fmaf_rn(sl[k].z, __fmul_rn(e4.z, -0.69314718055994531f), v[k].z);
+          o.w = __fmaf_rn(sl[k].w, __fmul_rn(e4.w, -0.69314718055994531f), v[k].w);
           store_out4<OutT>(outp, row * a.ld_out + (j << 2), o);
         }
       }

@@ -101,6 +101,14 @@ __device__ __forceinline__ float perturb_fma(float xn, uint32_t r, float c) {
   const float v = __uint_as_float(one_m) - 0.99999994039535522f;
   return __fmaf_rn(lg2_ftz(v), __uint_as_float(cs), xn);
 }
+// lg2(v) with the Laplace sign of r folded into its sign bit: perturb_fma(xn, r, c) == fma(signed_lg2_from_bits(r), c, xn)
+// bit for bit (flipping the sign of either factor of a product gives the same result)
+__device__ __forceinline__ float signed_lg2_from_bits(uint32_t r) {
+  uint32_t one_m;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(one_m) : "r"(r), "r"(0x7FFFFFu), "r"(0x3F800000u));
+  const float l = lg2_ftz(__uint_as_float(one_m) - 0.99999994039535522f);
+  return __uint_as_float(__float_as_uint(l) ^ (r & 0x80000000u));
+}
 __device__ __forceinline__ float laplace_from_bits(uint32_t r) {
   return laplace_scaled_from_bits(r, -0.69314718055994531f);
 }

@@ -245,7 +245,7 @@ def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed
         assert gum.is_contiguous() and gum.numel() == M * 2 * B * D
     s_coef = 0 if w is None or w.dim() == 1 else w.stride(0)
     s_out = out.stride(0) if out.dim() == 3 else 0
-    _call(("perturb_fwd", B, D, M, _dt(out), noise_mode, int(bool(want_gate))), "pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
+    _call(("perturb_fwd", B, D, M, _dt(out), noise_mode, int(bool(want_gate)), int(M > 1 and not any(sx))), "pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
            int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
            out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
            _seeds_ptr(model_seeds, M), _stream())

@@ -541,6 +541,14 @@ def test_perturb_shared_batch_sweep_kernel_matches_single_model(dev, out_dtype):
                                               out_dtype=out_dtype, want_minmax=True)
         assert torch.equal(one.view(it), out[m].view(it))
         assert torch.equal(mn1, mn[m])
+    # an eps sweep at ONE seed (how the sweep grid lands on a GPU): the models share the noise computation inside the
+    # kernel, and each still equals its own single-model launch bit for bit
+    same = torch.tensor([55, 55, 9], dtype=torch.int64, device=dev)
+    out3, _, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, model_seeds=same, offset=2, row0=B, n_models=M,
+                                         out_dtype=out_dtype)
+    for m, sd in enumerate((55, 55, 9)):
+        one, _, _, _ = ops.perturb_gate_fwd(blocks, w[m], eh[m], noise_mode=L.NOISE_PHILOX, seed=sd, offset=2, row0=B, out_dtype=out_dtype)
+        assert torch.equal(one.view(it), out3[m].view(it))
     # arithmetic-progression seeds (no device array) take the same kernel
     out2, _, _, _ = ops.perturb_gate_fwd(blocks, w, eh, noise_mode=L.NOISE_PHILOX, seed=100, seed_step=7, offset=2, row0=B,
                                          n_models=M, out_dtype=out_dtype)
