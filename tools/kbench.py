@@ -90,6 +90,7 @@ def main():
     w, eh, deps = ops.dp_coeffs(DP, 2.718281828)
     w6, eh6, _ = ops.dp_coeffs(torch.zeros(6, D, device=dev), [1.105, 2.718, 20.09, 148.4, 2981.0, 22026.0])
     seeds6 = torch.arange(980616, 980622, dtype=torch.int64, device=dev)
+    seeds1x6 = torch.full((6,), 980616, dtype=torch.int64, device=dev)
     Xh6 = torch.empty(6, B, D, dtype=bf, device=dev)
     Xh = torch.empty(B, D, dtype=bf, device=dev)
     Xf = torch.empty(B, D, device=dev)
@@ -116,7 +117,10 @@ def main():
 
     cases = [
         ("perturb_fwd_philox_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh), B * D * 6, 0),
-        ("perturb_fwd_shared6_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w6, eh6, noise_mode=L.NOISE_PHILOX, model_seeds=seeds6, out=Xh6, n_models=6), 6 * B * D * 6, 0),
+        # one GPU's share of the eps x seed grid: six eps values at ONE seed (noise shared inside the kernel) ...
+        ("perturb_fwd_shared6_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w6, eh6, noise_mode=L.NOISE_PHILOX, model_seeds=seeds1x6, out=Xh6, n_models=6), B * D * (4 + 6 * 2), 0),
+        # ... and six different seeds (every model regenerates its own noise)
+        ("perturb_fwd_6seeds_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w6, eh6, noise_mode=L.NOISE_PHILOX, model_seeds=seeds6, out=Xh6, n_models=6), B * D * (4 + 6 * 2), 0),
         ("perturb_fwd_philox_f32", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xf), B * D * 8, 0),
         ("perturb_fwd_nonoise_bf16", lambda: ops.perturb_gate_fwd([x0, x1], None, None, noise_mode=L.NOISE_NONE, out=Xh), B * D * 6, 0),
         ("perturb_fwd_philox_gate_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh, want_gate=True), B * D * 6, 0),
