@@ -212,7 +212,7 @@ class TwoPassTrainer:
         loss, acc, pred_id, lab = cal_loss(pred, label)                    # :208
         loss.backward()                                                    # :211
         self.model_opt.step()                                              # :212
-        return float(loss), float(acc), pred_id
+        return float(loss.detach()), float(acc), pred_id
 
 
 def reference_step_cpu(blocks, label, p: HeadParams, epsilon, hard_noise_on_host: bool = True):
@@ -235,7 +235,7 @@ def reference_step_cpu(blocks, label, p: HeadParams, epsilon, hard_noise_on_host
         pred = F.linear(h2, p.Wc, p.bc)
         loss, acc, _, _ = cal_loss(pred, label)
         loss.backward()
-        out = (float(loss), float(acc))
+        out = (float(loss.detach()), float(acc))
     return out
 
 

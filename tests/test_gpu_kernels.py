@@ -263,7 +263,7 @@ def test_cls_ce_matches_cal_loss(dev, n_models, B, H):
         assert rel_err(res["logits"][m], pred.detach()) < RTOL
         assert torch.equal(res["pred"][m].cpu(), pid)                      # argmax: bit-exact
         st = res["stats"][m].cpu()
-        assert abs(float(st[0]) - float(loss)) < 1e-5 * max(1.0, float(loss))
+        assert abs(float(st[0]) - float(loss.detach())) < 1e-5 * max(1.0, float(loss.detach()))
         assert float(st[1]) == float((pid == labels).sum()) and abs(float(st[2]) - float(acc)) < 1e-6
         assert rel_err(res["dWc"][m], wc.grad) < 5e-5 and rel_err(res["dbc"][m], b_.grad) < 5e-5
         # dz = dL/d(pre-tanh); recomputed tanh from atanh loses a little, so 1e-4 here
