@@ -385,7 +385,7 @@ def run_ours(args):
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.workload == "dp64k" else "weak",
                 "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "models_per_gpu": M, "models_total": total_models, "batch_per_model": B,
-                           "feature_dims": list(dims), "hidden": HIDDEN, "eps": eps, "step": "reference two-pass step incl. both Adam updates",
+                           "feature_dims": list(dims), "hidden": HIDDEN, "eps": eps, "seeds": seeds, "step": "reference two-pass step incl. both Adam updates",
                            "l2": f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)",
                            "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce",
                            "host_path": "recorded call-plan replay" if eng.fast_replay else "python wrappers"},
