@@ -131,3 +131,47 @@ def test_dp_init_variants_follow_the_reference_formulas():
         variants.dp_init("nonsense", dims)
     grid = parallel.sweep_grid([1.0], n_seeds=2, variants=("newinit", "tt", None))
     assert len(grid) == 6 and [g["variant"] for g in grid[:3]] == ["newinit", "tt", None]
+
+
+def test_call_plan_logic_with_a_stub_library(monkeypatch):
+    """ops.CallPlan (recorded C-ABI call replay of the launch-bound regimes) without a GPU: per-step increments are
+    found by difference, input pointers are substituted by position, 32-bit counters wrap, hooks fire in place, and a
+    buffer pointer that moved between the recorded steps is refused."""
+    from eeg_multimodal_b200 import _lib, ops
+
+    issued = []
+
+    class Stub:
+        def __getattr__(self, name):
+            def fn(*args):
+                issued.append((name, args))
+                return 0
+            return fn
+
+    monkeypatch.setattr(_lib, "_lib", Stub())
+    # pgf_adam_step(p, g, m, v, shadow, n, step, lr, b1, b2, eps, grad_scale, stream); pgf_fill_zero(p, nbytes, stream)
+    def adam(p, step):
+        return (("adam",), "pgf_adam_step", (p, 200, 300, 400, None, 1000, step, 1e-3, 0.9, 0.999, 1e-8, 1.0, 77))
+    hook = (("hook",), None, ("grad",))
+    fill = (("fill",), "pgf_fill_zero", (900, 64, 77))
+    rec_a, rec_b = [fill, adam(100, 5), hook], [fill, adam(111, 7), hook]           # recorded two steps apart
+    plan = ops.CallPlan(rec_a, rec_b, {100: "params"}, {111: "params"}, steps_apart=2)
+    fired = []
+    plan.replay(3, {"params": 555}, hook=fired.append)
+    assert fired == ["grad"] and [n for n, _ in issued] == ["pgf_fill_zero", "pgf_adam_step"]
+    args = issued[1][1]
+    assert args[0] == 555 and args[6] == 8 and args[1:6] == (200, 300, 400, None, 1000)   # step 5 + 3 * (7-5)/2
+    # a 32-bit Philox offset wraps instead of overflowing the ctypes argument
+    sig = _lib.SIGNATURES["pgf_gemm_bf16_ddp"][1]
+    base = [1, 8, 2, 8, 1, 4, 4, 4, 42, 0xFFFFFFFE, 0, 3, 4, 64, 5, 0, 77]
+    assert len(base) == len(sig)
+    nxt = list(base)
+    nxt[9] = 0xFFFFFFFF
+    plan2 = ops.CallPlan([(("g",), "pgf_gemm_bf16_ddp", tuple(base))], [(("g",), "pgf_gemm_bf16_ddp", tuple(nxt))], {})
+    plan2.replay(3, {})
+    assert issued[-1][1][9] == 1
+    # an internal buffer that moved between the recordings cannot be replayed
+    with pytest.raises(RuntimeError, match="pointer argument"):
+        ops.CallPlan([adam(100, 5)], [adam(100, 6)[:2] + ((100, 201, 300, 400, None, 1000, 6, 1e-3, 0.9, 0.999, 1e-8, 1.0, 77),)], {})
+    with pytest.raises(RuntimeError, match="different call sequences"):
+        ops.CallPlan([fill], [fill, fill], {})
