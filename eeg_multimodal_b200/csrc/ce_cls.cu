@@ -117,6 +117,19 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
       if (col < a.H) *reinterpret_cast<float4*>(s_dsum + col) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  // MODE 0/1 have the registers to keep this lane's slice of Wc resident (MODE 2 spends them on the dWc accumulators
+  // and re-reads Wc from shared memory per row)
+  constexpr bool WREG = MODE != 2;
+  float4 wr0[WREG ? NV : 1], wr1[WREG ? NV : 1];
+  if (WREG) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      const bool ok = (j << 2) < a.H;
+      wr0[k] = ok ? s_w[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      wr1[k] = ok ? s_w[nvec + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   const float b0 = a.bc[model * a.sbc], b1 = a.bc[model * a.sbc + 1];
   const long long* labels = a.labels ? a.labels + model * a.slab : nullptr;  // NULL: logits/pred only
   float loss_sum = 0.f, correct = 0.f, db0 = 0.f, db1 = 0.f;
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     for (int k = 0; k < NV; ++k) {
       const int j = lane + 32 * k;
       if ((j << 2) < a.H) {
-        const float4 w0 = s_w[j], w1 = s_w[nvec + j];
+        const float4 w0 = WREG ? wr0[k] : s_w[j], w1 = WREG ? wr1[k] : s_w[nvec + j];
         z0 = fmaf(h[k].x, w0.x, z0); z0 = fmaf(h[k].y, w0.y, z0);
         z0 = fmaf(h[k].z, w0.z, z0); z0 = fmaf(h[k].w, w0.w, z0);
         z1 = fmaf(h[k].x, w1.x, z1); z1 = fmaf(h[k].y, w1.y, z1);
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
             dw1[k].z = fmaf(g1, h[k].z, dw1[k].z); dw1[k].w = fmaf(g1, h[k].w, dw1[k].w);
           }
           if (a.dz) {
-            const float4 w0 = s_w[j], w1 = s_w[nvec + j];
+            const float4 w0 = WREG ? wr0[k] : s_w[j], w1 = WREG ? wr1[k] : s_w[nvec + j];
             float4 d;
             d.x = fmaf(g0, w0.x, g1 * w1.x);
             d.y = fmaf(g0, w0.y, g1 * w1.y);
