@@ -45,6 +45,10 @@ SIGNATURES = {
     "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
     "pgf_colsum_workspace": (SZ, [I, I]),
     "pgf_colsum": (I, [P, I, LL, I, I, P, P, SZ, P]),
+    "pgf_prigumbel_coef": (I, [P, P, I, F, F, I, U64, U32, P, P, P]),
+    "pgf_prigumbel_fwd": (I, [P, LL, P, P, F, U64, U32, U64, P, LL, P, P, I, I, P]),
+    "pgf_prigumbel_bwd_workspace": (SZ, [I, I]),
+    "pgf_prigumbel_bwd": (I, [P, LL, P, P, LL, P, F, F, P, LL, P, I, I, I, P, SZ, P]),
 }
 
 _lib = None
@@ -67,7 +71,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful call (for the bench's `gpu_launches` count)
-LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2}
+LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
 launch_count = 0
 launch_by_name = {}
 

@@ -355,4 +355,50 @@ int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out,
   return colsum(x, dtype, ld, B, N, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int pgf_prigumbel_coef(const float* w, const float* gumbel, int H, float exp_eps, float tau, int hard,
+                       unsigned long long seed, unsigned int offset, float* coef, float* wloss, void* stream) {
+  PGF_CHECK_ARG(w && coef && wloss && H > 0 && (H % 4) == 0 && aligned16(coef), "pgf_prigumbel_coef: NULL argument or H not a multiple of 4");
+  PGF_CHECK_ARG(tau > 0.f, "pgf_prigumbel_coef: tau must be positive");
+  return prigumbel_coef(w, gumbel, H, exp_eps, tau, hard, seed, offset, coef, wloss, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_prigumbel_fwd(const float* z, long long ldz, const float* coef, const float* lap, float eps,
+                      unsigned long long seed, unsigned int offset, unsigned long long row0, float* out, long long ld_out,
+                      float* row_min, float* row_max, int B, int H, void* stream) {
+  if (B == 0) return PGF_OK;
+  PGF_CHECK_ARG(z && coef && out && B > 0 && H > 0, "pgf_prigumbel_fwd: NULL or non-positive argument");
+  PGF_CHECK_ARG((H % 4) == 0 && (ldz % 4) == 0 && (ld_out % 4) == 0 && aligned16(z) && aligned16(coef) && aligned16(out),
+                "pgf_prigumbel_fwd: H and leading dimensions must be multiples of 4, pointers 16-byte aligned");
+  PGF_CHECK_ARG(lap != nullptr || eps > 0.f, "pgf_prigumbel_fwd: eps must be positive in Philox mode");
+  PriGumbelArgs a;
+  a.z = z; a.ldz = ldz; a.coef = coef; a.lap = lap; a.inv_eps = lap ? 0.f : 1.0f / eps;
+  a.k0 = static_cast<unsigned int>(seed); a.k1 = static_cast<unsigned int>(seed >> 32); a.offset = offset; a.row0 = row0;
+  a.out = out; a.ld_out = ld_out; a.row_min = row_min; a.row_max = row_max; a.B = B; a.H = H;
+  return prigumbel_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+size_t pgf_prigumbel_bwd_workspace(int B, int H) {
+  if (B <= 0 || H <= 0) return 0;
+  return static_cast<size_t>(prigumbel_bwd_slabs(B)) * H * sizeof(float);
+}
+
+int pgf_prigumbel_bwd(const float* z, long long ldz, const float* coef, const float* dout, long long ld_dout,
+                      const float* wloss, float exp_eps, float wloss_scale, float* dz, long long ld_dz, float* dw,
+                      int accumulate, int B, int H, float* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return PGF_OK;
+  PGF_CHECK_ARG(z && coef && dout && dz && workspace && B > 0 && H > 0, "pgf_prigumbel_bwd: NULL or non-positive argument");
+  PGF_CHECK_ARG(dw == nullptr || wloss != nullptr, "pgf_prigumbel_bwd: dw needs wloss from pgf_prigumbel_coef");
+  PGF_CHECK_ARG((H % 4) == 0 && (ldz % 4) == 0 && (ld_dout % 4) == 0 && (ld_dz % 4) == 0 && aligned16(z) && aligned16(coef) &&
+                    aligned16(dout) && aligned16(dz),
+                "pgf_prigumbel_bwd: H and leading dimensions must be multiples of 4, pointers 16-byte aligned");
+  if (workspace_bytes < pgf_prigumbel_bwd_workspace(B, H)) {
+    set_error("pgf_prigumbel_bwd: workspace of %zu bytes, need %zu", workspace_bytes, pgf_prigumbel_bwd_workspace(B, H));
+    return PGF_ERR_WORKSPACE;
+  }
+  PriGumbelBwdArgs a;
+  a.z = z; a.ldz = ldz; a.coef = coef; a.dout = dout; a.ld_dout = ld_dout; a.dz = dz; a.ld_dz = ld_dz; a.partial = workspace;
+  a.B = B; a.H = H;
+  return prigumbel_bwd(a, exp_eps, wloss_scale, wloss, dw, accumulate, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

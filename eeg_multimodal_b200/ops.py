@@ -502,3 +502,57 @@ def colsum(x, out=None):
     ws = workspace("colsum").get(nbytes, x.device)
     _call(("colsum", B, N, _dt(x)), "pgf_colsum", x.data_ptr(), _dt(x), x.stride(0), B, N, out.data_ptr(), ws.data_ptr(), ws.numel() * 4, _stream())
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# the older PriGumbel head tail (SURVEY 8 row a-alt; train_val.py:80-123)
+def prigumbel_coef(w, *, exp_eps, tau, hard, gumbel=None, seed=0, offset=0, coef=None, wloss=None):
+    """Per-forward column coefficients of gumbel_dropout (train_val.py:95-101) and the w term of loss_function
+    (train_val.py:88-89).  gumbel [H,2] injects the draw; None = Philox(seed, offset).  Returns (coef [4,H], wloss [2])."""
+    _chk(w, torch.float32, "w")
+    H = w.shape[0]
+    if gumbel is not None:
+        _chk(gumbel, torch.float32, "gumbel")
+        if tuple(gumbel.shape) != (H, 2) or not gumbel.is_contiguous():
+            raise ValueError("gumbel must be a contiguous [H,2] tensor (the shape F.gumbel_softmax draws, train_val.py:99)")
+    if coef is None:
+        coef = torch.empty((4, H), dtype=torch.float32, device=w.device)
+    if wloss is None:
+        wloss = torch.empty(2, dtype=torch.float32, device=w.device)
+    _call(("prigumbel_coef", H), "pgf_prigumbel_coef", w.data_ptr(), _ptr(gumbel), H, float(exp_eps), float(tau), int(bool(hard)),
+          int(seed), int(offset) & 0xFFFFFFFF, coef.data_ptr(), wloss.data_ptr(), _stream())
+    return coef, wloss
+
+
+def prigumbel_fwd(z, coef, *, eps, lap=None, seed=0, offset=0, row0=0, out=None, want_minmax=False):
+    """gumbel_dropout + Lap_noise (train_val.py:95-101,114-123) on fc2's output z [B,H].  lap [B] injects the
+    Laplace(0,1/eps) row draws; None = Philox(seed, offset, row0 + b)."""
+    _chk(z, torch.float32, "z")
+    B, H = z.shape
+    if lap is not None:
+        _chk(lap, torch.float32, "lap")
+        if lap.numel() != B or not lap.is_contiguous():
+            raise ValueError("lap must hold one Laplace(0,1/eps) draw per row (train_val.py:121)")
+    if out is None:
+        out = torch.empty((B, H), dtype=torch.float32, device=z.device)
+    mn = torch.empty(B, dtype=torch.float32, device=z.device) if want_minmax else None
+    mx = torch.empty(B, dtype=torch.float32, device=z.device) if want_minmax else None
+    _call(("prigumbel_fwd", B, H), "pgf_prigumbel_fwd", z.data_ptr(), z.stride(0), coef.data_ptr(), _ptr(lap), float(eps), int(seed),
+          int(offset) & 0xFFFFFFFF, int(row0), out.data_ptr(), out.stride(0), _ptr(mn), _ptr(mx), B, H, _stream())
+    return (out, mn, mx) if want_minmax else out
+
+
+def prigumbel_bwd(z, coef, dout, *, wloss=None, exp_eps=1.0, wloss_scale=1.0, dz=None, dw=None, want_dw=True, accumulate=False):
+    """Autograd of prigumbel_fwd (+ the w term of loss_function): returns (dz [B,H], dw [H] or None)."""
+    _chk(z, torch.float32, "z"); _chk(dout, torch.float32, "dout")
+    B, H = z.shape
+    if dz is None:
+        dz = torch.empty((B, H), dtype=torch.float32, device=z.device)
+    if dw is None and want_dw:
+        dw = torch.zeros(H, dtype=torch.float32, device=z.device) if accumulate else torch.empty(H, dtype=torch.float32, device=z.device)
+    nbytes = _query("pgf_prigumbel_bwd_workspace", B, H)
+    ws = workspace("prigumbel").get(nbytes, z.device)
+    _call(("prigumbel_bwd", B, H), "pgf_prigumbel_bwd", z.data_ptr(), z.stride(0), coef.data_ptr(), dout.data_ptr(), dout.stride(0),
+          _ptr(wloss), float(exp_eps), float(wloss_scale), dz.data_ptr(), dz.stride(0), _ptr(dw), int(bool(accumulate)), B, H,
+          ws.data_ptr(), ws.numel() * 4, _stream())
+    return dz, dw

@@ -206,6 +206,30 @@ size_t pgf_colsum_workspace(int B, int N);
 int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out, float* workspace,
                size_t workspace_bytes, void* stream);
 
+/* ---- (a-alt) the OLDER PriGumbel head tail: Gumbel dropout + row Laplace + w-loss, fwd and bwd ----
+ * replaces: gumbel_dropout (train_val.py:95-101), Lap_noise (train_val.py:114-123), the w term of
+ *           loss_function (train_val.py:80-93: max_j((1-w_j) e^eps + w_j)) and their autograd, i.e. what
+ *           sits between fc2 and the classifier in train_val.py:151-157.
+ * coef:  per-forward column coefficients from w [H] and ONE [H,2] Gumbel draw (NULL = Philox:
+ *        counter (j/4, 0, Gumbel plane, offset)); hard = eval mode (straight-through composite),
+ *        soft = train mode (train_val.py:108-111).  coef [4,H] = {mask, 1-w, d mask/d w, soft y1};
+ *        wloss [2] = {max_j((1-w_j) e^eps + w_j), its arg-max}.
+ * fwd:   out[b,:] = minmax_row((z[b,:] * mask) / (1-w)) + n_b, n_b = lap[b] (injected Laplace(0,1/eps)
+ *        draws) or Philox: counter (0, row0+b, Laplace, offset), scaled by 1/eps.
+ * bwd:   dz [B,H] (gradient of fc2's output, full min-max backward with torch's first-occurrence
+ *        arg-min/arg-max routing) and, when dw != NULL, dw [H] (+= if accumulate) = gradient through
+ *        the gate, through 1/(1-w), and wloss_scale * d wloss/dw (1 - e^eps at the arg-max).
+ *        workspace: pgf_prigumbel_bwd_workspace(B,H) bytes, fixed-order reduction, no atomics.      */
+int pgf_prigumbel_coef(const float* w, const float* gumbel, int H, float exp_eps, float tau, int hard,
+                       unsigned long long seed, unsigned int offset, float* coef, float* wloss, void* stream);
+int pgf_prigumbel_fwd(const float* z, long long ldz, const float* coef, const float* lap, float eps,
+                      unsigned long long seed, unsigned int offset, unsigned long long row0, float* out,
+                      long long ld_out, float* row_min, float* row_max, int B, int H, void* stream);
+size_t pgf_prigumbel_bwd_workspace(int B, int H);
+int pgf_prigumbel_bwd(const float* z, long long ldz, const float* coef, const float* dout, long long ld_dout,
+                      const float* wloss, float exp_eps, float wloss_scale, float* dz, long long ld_dz, float* dw,
+                      int accumulate, int B, int H, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

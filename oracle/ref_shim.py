@@ -134,3 +134,67 @@ def real_feature_blocks(n_rows: int = 8, seed: int = 980616):
                                      tgt_key_padding_mask=act_mask == 0, memory_key_padding_mask=am == 0)
         cm = cm.permute(1, 0, 2).mean(dim=1)
     return pooled.contiguous(), emb.squeeze(1).contiguous(), cm.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# the older PriGumbel head (SURVEY.md section 8 row a-alt): train_val.py at the reference root
+# ----------------------------------------------------------------------------------------------
+def import_reference_train_val():
+    """Import the reference's train_val.py unchanged.  Shimmed outside the file: `opacus` (unused by this
+    path) and `transformers.AdamW` (removed from transformers 5; imported, never used).  Importing it sets
+    CUDA_VISIBLE_DEVICES and seeds the global RNGs (train_val.py:20,35); the env change is undone."""
+    if "opacus" not in sys.modules:
+        sys.modules["opacus"] = types.SimpleNamespace(PrivacyEngine=object)
+    import transformers
+
+    if not hasattr(transformers, "AdamW"):
+        transformers.AdamW = object
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    saved = os.environ.get("CUDA_VISIBLE_DEVICES")
+    import train_val  # the reference file, read in place
+
+    if saved is None:
+        os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+    else:
+        os.environ["CUDA_VISIBLE_DEVICES"] = saved
+    return train_val
+
+
+class ShimmedPriGumbelHead:
+    """train_val.ConcatModel with stub encoders: `forward` runs the reference's own lines 144-157
+    (gumbel_dropout, Lap_noise included) and `loss` its own loss_function (train_val.py:80-93)."""
+
+    def __init__(self, tau: float, epsilon: float):
+        self.tv = tv = import_reference_train_val()
+        cls = tv.ConcatModel
+        m = cls.__new__(cls)
+        nn.Module.__init__(m)
+        # the attributes ConcatModel.__init__ (train_val.py:126-140) creates, minus the encoders
+        m.bert, m.visual_encoder, m.multi_head_decoder = _StubBert(), _StubVisual(), _StubDecoder()
+        m.w = nn.parameter.Parameter(data=torch.rand(768))
+        m.dropout = tv.GumbelSoftmaxDropout(tau)
+        m.fc1 = nn.Linear(768 * 3, 768 * 3)
+        m.fc2 = nn.Linear(768 * 3, 768)
+        m.classifier = nn.Linear(768, 2)
+        m.epsilon = epsilon
+        self.model = m
+
+    def load(self, p):
+        sd = {"fc1.weight": p.W1, "fc1.bias": p.b1, "fc2.weight": p.W2, "fc2.bias": p.b2,
+              "classifier.weight": p.Wc, "classifier.bias": p.bc, "w": p.w}
+        self.model.load_state_dict(sd, strict=True)
+
+    def forward(self, blocks, seed: int, train: bool):
+        """Seed the global RNG, then call the reference forward: it draws the Gumbel exponential [768,2] and the
+        Laplace uniform [B,1] itself, in that order; train mode = soft gate, eval mode = hard gate."""
+        eeg, act, cm = blocks
+        m = self.model.train(train)
+        m.bert.block, m.visual_encoder.block, m.multi_head_decoder.block = eeg, act, cm
+        B = eeg.shape[0]
+        torch.manual_seed(seed)
+        return m(act.new_zeros(B, 1, 512), torch.ones(B, 1, dtype=torch.long), torch.zeros(B, 4, dtype=torch.long),
+                 torch.ones(B, 4, dtype=torch.long))
+
+    def loss(self, prediction, label, alpha: float):
+        return self.tv.loss_function(prediction, label, self.model, alpha, self.model.epsilon)
