@@ -115,7 +115,15 @@ def main():
     ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh)
     ops.gemm_bf16(Xh, W1, H1, M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1)
 
+    # the older PriGumbel head tail (train_val.py:95-123) at the same batch: z = fc2 output [B,H] fp32
+    pg_w = torch.rand(H, device=dev, generator=g) * 0.9 + 0.05
+    pg_coef, pg_wloss = ops.prigumbel_coef(pg_w, exp_eps=2.718, tau=0.1, hard=False, seed=1)
+    pg_out, pg_dz, pg_dw = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev), torch.empty(H, device=dev)
+    pg_dout = torch.randn(B, H, device=dev, generator=g) / B
+
     cases = [
+        ("prigumbel_fwd", lambda: ops.prigumbel_fwd(H2, pg_coef, eps=1.0, seed=1, out=pg_out), B * H * 8, 0),
+        ("prigumbel_bwd", lambda: ops.prigumbel_bwd(H2, pg_coef, pg_dout, wloss=pg_wloss, exp_eps=2.718, dz=pg_dz, dw=pg_dw), B * H * 12, 0),
         ("perturb_fwd_philox_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w, eh, noise_mode=L.NOISE_PHILOX, seed=1, out=Xh), B * D * 6, 0),
         # one GPU's share of the eps x seed grid: six eps values at ONE seed (noise shared inside the kernel) ...
         ("perturb_fwd_shared6_bf16", lambda: ops.perturb_gate_fwd([x0, x1], w6, eh6, noise_mode=L.NOISE_PHILOX, model_seeds=seeds1x6, out=Xh6, n_models=6), B * D * (4 + 6 * 2), 0),
