@@ -122,22 +122,29 @@ def run(cfg) -> dict:
         vm = [EpochMeter() for _ in mine]
         accs = torch.zeros(len(mine), cfg.n_eval)
         f1s = torch.zeros(len(mine), cfg.n_eval)
-        preds = [[[] for _ in range(cfg.n_eval)] for _ in mine]
-        labs = []
+        # everything stays on the device while the evaluation launches are queued; ONE transfer per epoch
+        preds = [[] for _ in range(cfg.n_eval)]                        # per repetition: list of [M,B] predictions
+        labs, first_stats = [], []
         for blocks, labels in val_loader:
-            labs.append(labels.cpu())
+            labs.append(labels.reshape(-1))
             for e in range(cfg.n_eval):                               # train.py:126-131
                 ev = eng.eval_step(blocks, labels)
-                for k in range(len(mine)):
-                    preds[k][e].append(ev["pred"][k].cpu())
-                    if e == 0:
-                        vm[k].update(float(ev["loss"][k]), float(ev["acc"][k]), ev["pred"][k], labels)
-        lab = torch.cat(labs)
+                preds[e].append(ev["pred"].view(len(mine), -1).clone())
+                if e == 0:
+                    first_stats.append(torch.stack((ev["loss"], ev["acc"]), dim=1).clone())
+        lab = torch.cat(labs).cpu()
+        preds = [torch.cat(p, dim=1).cpu() for p in preds]           # n_eval x [M, N]
+        first_stats = torch.stack(first_stats).cpu().tolist()         # [batches][M][2]
+        lo = 0
+        for bi, l in enumerate(labs):                                 # epoch meters: unweighted per-batch means (past_acc.py:236)
+            hi = lo + l.numel()
+            for k in range(len(mine)):
+                vm[k].update(first_stats[bi][k][0], first_stats[bi][k][1], preds[0][k, lo:hi], lab[lo:hi])
+            lo = hi
         for k in range(len(mine)):
             for e in range(cfg.n_eval):
-                p = torch.cat(preds[k][e])
-                accs[k, e] = (p == lab).float().mean()
-                f1s[k, e] = binary_f1(p, lab)
+                accs[k, e] = (preds[e][k] == lab).float().mean()
+                f1s[k, e] = binary_f1(preds[e][k], lab)
         info = f"Eval  Epoch: {epoch:3d}"
         if "Accuracy" in want:
             info += f" | Accuracy: {accs.mean().item():5.2f}"
