@@ -19,7 +19,7 @@ constexpr int PG_WARPS = PG_THREADS / 32;
 
 // ---- per-column coefficients: one CTA --------------------------------------------------------------------------------
 // coef [4,H]: 0 mask_j (soft y1, or the straight-through composite (onehot1 - y1) + y1), 1 (1 - w_j), 2 d mask_j / d w_j
-// (softmax backward of both planes, torch's operation order), 3 soft y1.  wloss[0] = max_j((1-w_j) e^eps + w_j), wloss[1] = argmax.
+// (softmax backward of both planes, torch's operation order), 3 1/(1-w) (only used for vanishing numerators, see div_rn_z).  wloss[0] = max_j((1-w_j) e^eps + w_j), wloss[1] = argmax.
 __global__ void __launch_bounds__(PG_THREADS) prigumbel_coef_kernel(const float* __restrict__ w, const float* __restrict__ gum,
                                                                     int H, float exp_eps, float tau, int hard,
                                                                     unsigned int k0, unsigned int k1, unsigned int offset,
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(PG_THREADS) prigumbel_coef_kernel(const float*
     coef[j] = mask;
     coef[H + j] = omw;
     coef[2 * H + j] = dmask;
-    coef[3 * H + j] = y1;
+    coef[3 * H + j] = __frcp_rn(omw);
     const float t = omw * exp_eps + wj;
     if (t > best) { best = t; besti = j; }
   }
@@ -73,6 +73,18 @@ __global__ void __launch_bounds__(PG_THREADS) prigumbel_coef_kernel(const float*
   }
 }
 
+// IEEE division with a short-cut for zero / vanishing numerators: at the reference's tau = 0.01 the gate is 0 on about half of the
+// columns, and 0 / x takes the slow path of __fdiv_rn (the same effect as in the Adam kernel).
+// 0 / x = 0 with the numerator's sign for any finite positive or negative x != 0; x = 0 or NaN falls through to the division.
+// In train mode (soft gate) the same columns carry masks like e^-95: the products are denormal, which is the other slow path
+// of __fdiv_rn.  Below 2^-100 the quotient is formed as num * (1/den) (FMUL handles denormals at full rate); after the row
+// min-max normalisation such an entry is indistinguishable from 0 in fp32 either way.
+__device__ __forceinline__ float div_rn_z(float num, float den, float inv_den) {
+  return (fabsf(num) < 7.9e-31f && den > 0.f) ? num * inv_den : __fdiv_rn(num, den);
+}
+
+__device__ __forceinline__ float div0(float num, float den) { return (num == 0.f && den > 0.f) ? num : __fdiv_rn(num, den); }
+
 // r = (z * mask) / (1 - w), the reference's operation order; row arg-min / arg-max, first occurrence on ties.
 template <int NV>
 __device__ __forceinline__ void dropout_row(const float* __restrict__ zrow, const float* __restrict__ coef, int H, int lane,
@@ -85,8 +97,9 @@ __device__ __forceinline__ void dropout_row(const float* __restrict__ zrow, cons
       z[k] = *reinterpret_cast<const float4*>(zrow + col);
       const float4 m4 = *reinterpret_cast<const float4*>(coef + col);
       const float4 o4 = *reinterpret_cast<const float4*>(coef + H + col);
-      r[k] = make_float4(__fdiv_rn(z[k].x * m4.x, o4.x), __fdiv_rn(z[k].y * m4.y, o4.y), __fdiv_rn(z[k].z * m4.z, o4.z),
-                         __fdiv_rn(z[k].w * m4.w, o4.w));
+      const float4 i4 = *reinterpret_cast<const float4*>(coef + 3 * H + col);
+      r[k] = make_float4(div_rn_z(z[k].x * m4.x, o4.x, i4.x), div_rn_z(z[k].y * m4.y, o4.y, i4.y),
+                         div_rn_z(z[k].z * m4.z, o4.z, i4.z), div_rn_z(z[k].w * m4.w, o4.w, i4.w));
       const float e[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -127,8 +140,9 @@ __global__ void __launch_bounds__(PG_THREADS) prigumbel_fwd_kernel(const PriGumb
     for (int k = 0; k < NV; ++k) {
       const int col = (lane + 32 * k) << 2;
       if (col < a.H) {
-        const float4 o = make_float4(__fdiv_rn(r[k].x - mn, range) + noise, __fdiv_rn(r[k].y - mn, range) + noise,
-                                     __fdiv_rn(r[k].z - mn, range) + noise, __fdiv_rn(r[k].w - mn, range) + noise);
+        // (the row's minimum itself is an exact 0 / range: same short-cut)
+        const float4 o = make_float4(div0(r[k].x - mn, range) + noise, div0(r[k].y - mn, range) + noise,
+                                     div0(r[k].z - mn, range) + noise, div0(r[k].w - mn, range) + noise);
         *reinterpret_cast<float4*>(a.out + row * a.ld_out + col) = o;
       }
     }
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(PG_THREADS) prigumbel_fwd_kernel(const PriGumb
 // dz = dr * mask / (1 - w) with dr the min-max backward of dout; per-CTA column partials of A_j = sum_b dr_bj * z_bj
 // (the only batch reduction the gradient of w needs: d mask_j = A_j / (1-w_j), and through the division A_j mask_j / (1-w_j)^2).
 template <int NV>
-__global__ void __launch_bounds__(PG_THREADS) prigumbel_bwd_kernel(const PriGumbelBwdArgs a) {
+__global__ void __launch_bounds__(PG_THREADS, NV <= 6 ? 2 : 1) prigumbel_bwd_kernel(const PriGumbelBwdArgs a) {
   extern __shared__ float s_acc[];   // [PG_WARPS][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 acc[NV];
@@ -185,9 +199,10 @@ __global__ void __launch_bounds__(PG_THREADS) prigumbel_bwd_kernel(const PriGumb
         }
         const float4 m4 = *reinterpret_cast<const float4*>(a.coef + col);
         const float4 o4 = *reinterpret_cast<const float4*>(a.coef + a.H + col);
+        const float4 i4 = *reinterpret_cast<const float4*>(a.coef + 3 * a.H + col);
         *reinterpret_cast<float4*>(a.dz + row * a.ld_dz + col) =
-            make_float4(__fdiv_rn(dr[0] * m4.x, o4.x), __fdiv_rn(dr[1] * m4.y, o4.y), __fdiv_rn(dr[2] * m4.z, o4.z),
-                        __fdiv_rn(dr[3] * m4.w, o4.w));
+            make_float4(div_rn_z(dr[0] * m4.x, o4.x, i4.x), div_rn_z(dr[1] * m4.y, o4.y, i4.y),
+                        div_rn_z(dr[2] * m4.z, o4.z, i4.z), div_rn_z(dr[3] * m4.w, o4.w, i4.w));
         acc[k].x = fmaf(dr[0], z[k].x, acc[k].x);
         acc[k].y = fmaf(dr[1], z[k].y, acc[k].y);
         acc[k].z = fmaf(dr[2], z[k].z, acc[k].z);
@@ -233,9 +248,9 @@ int dispatch_nv(int H, F&& f) {
   return PGF_ERR_UNSUPPORTED;
 }
 
-int row_grid(int B) {
+int row_grid(int B, int ctas_per_sm = 2) {
   long long g = (static_cast<long long>(B) + PG_WARPS - 1) / PG_WARPS;
-  const long long cap = 2LL * num_sms();
+  const long long cap = static_cast<long long>(ctas_per_sm) * num_sms();
   if (g > cap) g = cap;
   return g < 1 ? 1 : static_cast<int>(g);
 }
@@ -252,7 +267,9 @@ int prigumbel_coef(const float* w, const float* gum, int H, float exp_eps, float
 
 int prigumbel_fwd(const PriGumbelArgs& a, cudaStream_t s) {
   return dispatch_nv(a.H, [&](auto nv) {
-    prigumbel_fwd_kernel<decltype(nv)::value><<<row_grid(a.B), PG_THREADS, 0, s>>>(a);
+    auto* k = &prigumbel_fwd_kernel<decltype(nv)::value>;
+    const int occ = cached_occupancy(reinterpret_cast<const void*>(k), PG_THREADS, 0, 2);
+    k<<<row_grid(a.B, occ), PG_THREADS, 0, s>>>(a);
     PGF_CUDA_LAUNCH_CHECK("pgf_prigumbel_fwd");
     return PGF_OK;
   });

@@ -212,7 +212,7 @@ int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out,
  *           sits between fc2 and the classifier in train_val.py:151-157.
  * coef:  per-forward column coefficients from w [H] and ONE [H,2] Gumbel draw (NULL = Philox:
  *        counter (j/4, 0, Gumbel plane, offset)); hard = eval mode (straight-through composite),
- *        soft = train mode (train_val.py:108-111).  coef [4,H] = {mask, 1-w, d mask/d w, soft y1};
+ *        soft = train mode (train_val.py:108-111).  coef [4,H] = {mask, 1-w, d mask/d w, 1/(1-w)};
  *        wloss [2] = {max_j((1-w_j) e^eps + w_j), its arg-max}.
  * fwd:   out[b,:] = minmax_row((z[b,:] * mask) / (1-w)) + n_b, n_b = lap[b] (injected Laplace(0,1/eps)
  *        draws) or Philox: counter (0, row0+b, Laplace, offset), scaled by 1/eps.

@@ -117,7 +117,7 @@ def main():
 
     # the older PriGumbel head tail (train_val.py:95-123) at the same batch: z = fc2 output [B,H] fp32
     pg_w = torch.rand(H, device=dev, generator=g) * 0.9 + 0.05
-    pg_coef, pg_wloss = ops.prigumbel_coef(pg_w, exp_eps=2.718, tau=0.1, hard=False, seed=1)
+    pg_coef, pg_wloss = ops.prigumbel_coef(pg_w, exp_eps=2.718, tau=0.01, hard=False, seed=1)   # the reference's tau (train_val.py:524)
     pg_out, pg_dz, pg_dw = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev), torch.empty(H, device=dev)
     pg_dout = torch.randn(B, H, device=dev, generator=g) / B
 
