@@ -299,7 +299,11 @@ def run_ours(args):
     fence()
     sampler.active = True
     _lib.launch_count = 0
-    ops.TIMING = []
+    # Launch-bound workloads (call-plan replay): bracketing every C-ABI call with CUDA events costs ~20 % of the step there,
+    # so the timed K steps run uninstrumented and the per-kernel events come from a second pass of K steps right after.
+    # GPU-bound workloads keep the events inside the timed region itself.
+    split_events = bool(eng.fast_replay)
+    ops.TIMING = None if split_events else []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
@@ -307,9 +311,19 @@ def run_ours(args):
     e1.record()
     fence()
     launches = _lib.launch_count
+    ms = e0.elapsed_time(e1)
+    ms_events = ms
+    if split_events:
+        ops.TIMING = []
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(K):
+            step(W + K + i)
+        e3.record()
+        fence()
+        ms_events = e2.elapsed_time(e3)
     timing = ops.TIMING
     ops.TIMING = None
-    ms = e0.elapsed_time(e1)
     sampler.active = False
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -323,7 +337,7 @@ def run_ours(args):
 
     # ---- per-kernel rooflines from the timed region's own CUDA events (every launch is bracketed)
     peaks, peak_kind = measured_peaks()
-    kernels, roofline = kernel_table(timing, ms, K, peaks, peak_kind)
+    kernels, roofline = kernel_table(timing, ms_events, K, peaks, peak_kind)
     if roofline is not None and precision == "bf16":
         roofline["step_tensor_frac"] = flops_per_sample_step(D, HIDDEN) * B * M * K / (ms * 1e-3) / 1e12 / roofline["peak"] \
             if roofline["bound"] == "tensor" else None
@@ -358,7 +372,7 @@ def run_ours(args):
                 torch.cuda.current_stream().wait_event(ready[s])
                 st = eng.train_step(devbuf[s][0], devbuf[s][1], row0=i * B, global_batch=global_batch, grad_hook=hook)
                 freed[s].record()
-                loss_host[:, :3].copy_(torch.stack([st["loss"], st["n_correct"], st["acc"]], 1), non_blocking=True)
+                loss_host.copy_(st["stats"], non_blocking=True)             # per-model {loss, n_correct, accuracy, B}
             torch.cuda.synchronize()
 
         e2e_loop(2, 0)
@@ -373,7 +387,7 @@ def run_ours(args):
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         h2d = sum(B * d * 4 for d in dims) + B * 8
         e2e = {"value": samples_per_step * K / (float(ems) * 1e-3), "unit": "model-samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": M * 3 * 4, "ms_per_step": float(ems) / K}
+               "d2h_bytes_per_step": M * 4 * 4, "ms_per_step": float(ems) / K}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -386,9 +400,12 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "models_per_gpu": M, "models_total": total_models, "batch_per_model": B,
                            "feature_dims": list(dims), "hidden": HIDDEN, "eps": eps, "seeds": seeds, "step": "reference two-pass step incl. both Adam updates",
-                           "l2": f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)",
+                           "l2": (f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)" if B >= 4096 else
+                                  f"per-step working set = weights + Adam state of {M} models = {M * eng.P * 16 / 1e6:.0f} MB >> 126 MB L2 "
+                                  f"(the {sum(dims) * B * 4 / 1e3:.0f} KB batch is not what is streamed)"),
                            "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce",
-                           "host_path": "recorded call-plan replay" if eng.fast_replay else "python wrappers"},
+                           "host_path": "recorded call-plan replay" if eng.fast_replay else "python wrappers",
+                           "kernel_events": "second pass of K steps (launch-bound workload)" if split_events else "inside the timed region"},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
                 "loss_last": [float(x) for x in st["loss"].cpu()]}
         print(json.dumps(line))

@@ -396,7 +396,7 @@ class HeadEngine:
         """Per-model statistics of pass 2 as fresh tensors (the kernels write into persistent buffers that the next
         step overwrites)."""
         st = stats.view(self.M, 4).clone()
-        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1])
+        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], stats=st)   # stats [M,4] = {loss, n_correct, acc, B}
 
     @torch.no_grad()
     def eval_step(self, blocks, labels, row0=0):
