@@ -302,7 +302,7 @@ def run_ours(args):
     # Launch-bound workloads (call-plan replay): bracketing every C-ABI call with CUDA events costs ~20 % of the step there,
     # so the timed K steps run uninstrumented and the per-kernel events come from a second pass of K steps right after.
     # GPU-bound workloads keep the events inside the timed region itself.
-    split_events = bool(eng.fast_replay)
+    split_events = bool(eng.fast_replay) or os.environ.get("PGF_BENCH_SPLIT_EVENTS") == "1"
     ops.TIMING = None if split_events else []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
