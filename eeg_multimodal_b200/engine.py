@@ -326,7 +326,7 @@ class HeadEngine:
         labels = self._labels(labels)
         blocks = [b.contiguous() for b in blocks]
         key = (tuple((tuple(b.shape), tuple(b.stride()), b.dtype) for b in blocks), tuple(labels.shape), tuple(labels.stride()),
-               global_batch, bool(dp_pass), grad_hook is not None)
+               global_batch, bool(dp_pass), grad_hook is not None, ops._stream())   # a plan replays on the stream it was recorded on
         ent = self._plans.get(key)
         inputs = {("block", i): b.data_ptr() for i, b in enumerate(blocks)}
         inputs["labels"] = labels.data_ptr()

@@ -174,7 +174,9 @@ class CallPlan:
 
 
 def workspace(tag: str) -> Workspace:
-    return _ws.setdefault(tag, Workspace())
+    """Scratch buffer of one op ON THE LAUNCHING STREAM: work issued on different streams (independent engines whose
+    kernels overlap) must not share scratch, work on one stream is ordered and may."""
+    return _ws.setdefault((tag, _stream()), Workspace())
 
 
 # --------------------------------------------------------------------------------------------

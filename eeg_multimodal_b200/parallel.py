@@ -78,3 +78,56 @@ def gather_metrics(local: dict, group=None):
     for d in out:
         merged.update(d)
     return dict(sorted(merged.items()))
+
+
+class StreamedEnsemble:
+    """One GPU's share of a sweep as G independent model groups (HeadEngines), each on its own CUDA stream.
+
+    At the reference's batch of 8 a step is ~14 kernels of 10-150 us; with few models per GPU each of them spends a
+    visible part of its life ramping up and draining.  Independent groups issued on separate streams fill each other's
+    ramp-up and tail.  Measured (bench.py --workload sweep48_b8 --streams 2): +1.5 % at 48 and at 128 models per GPU; at
+    6 models per GPU the fork/join events and stream switches of this class cost more host time than the overlap returns
+    (-5 %; a bare two-stream loop gains 4.7 % there, tools/stream_overlap_probe.py), so it is opt-in.
+    The models stay exactly the models of the sweep grid: a group is a contiguous slice of the GPU's model list, every
+    kernel, seed and Philox offset is what the single-engine path uses, so results are bit-identical to it.
+
+    `train_step` / `eval_step` take the caller's batch on the caller's current stream: the group streams wait for
+    whatever the caller has queued before (the batch upload), and -- unless join=False -- the caller's stream waits for
+    the groups before the concatenated statistics are returned.  With join=False the per-group results are returned
+    as a list and the caller joins later (`join()`), which lets consecutive steps of different groups overlap."""
+
+    def __init__(self, engines):
+        if not engines:
+            raise ValueError("StreamedEnsemble needs at least one engine")
+        self.engines = list(engines)
+        self.streams = [torch.cuda.Stream(device=e.device) for e in self.engines]
+        self.M = sum(e.M for e in self.engines)
+        self._fork = torch.cuda.Event()
+
+    def _run(self, method, blocks, labels, join, kw):
+        cur = torch.cuda.current_stream()
+        self._fork.record(cur)
+        outs = []
+        for e, s in zip(self.engines, self.streams):
+            s.wait_event(self._fork)
+            with torch.cuda.stream(s):
+                outs.append(getattr(e, method)(blocks, labels, **kw))
+        if not join:
+            return outs
+        self.join()
+        for o in outs:
+            for t in o.values():
+                if torch.is_tensor(t):
+                    t.record_stream(cur)          # allocated on a group stream, consumed on the caller's
+        return {k: torch.cat([o[k] for o in outs]) for k in outs[0] if torch.is_tensor(outs[0][k])}
+
+    def train_step(self, blocks, labels, join=True, **kw):
+        return self._run("train_step", blocks, labels, join, kw)
+
+    def eval_step(self, blocks, labels, join=True, **kw):
+        return self._run("eval_step", blocks, labels, join, kw)
+
+    def join(self):
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)

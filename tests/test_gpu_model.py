@@ -336,3 +336,38 @@ def test_engine_bf16_path_learns_and_matches_fp32_path(dev):
         assert float(eng.DP.abs().max()) > 0
     rel = (hist["bf16"] - hist["fp32"]).abs() / hist["fp32"].abs().clamp_min(1e-3)
     assert float(rel.max()) < 5e-2, float(rel.max())      # trajectories agree step by step
+
+
+def test_streamed_ensemble_is_bit_identical_to_sequential_engines(dev):
+    """parallel.StreamedEnsemble: two model groups on two CUDA streams (kernels overlap) against the same two engines
+    stepped one after the other on one stream -- parameters bit-identical after 6 steps, with and without call-plan
+    replay.  (Scratch buffers are per stream: shared scratch between overlapping engines would race.)"""
+    from eeg_multimodal_b200 import HeadEngine, parallel
+
+    dims = (768, 768, 768)
+    g = torch.Generator().manual_seed(5)
+    blocks = [torch.rand(8, d, generator=g).to(dev) for d in dims]
+    labels = (torch.rand(8, generator=g) < 0.66).long().to(dev)
+    for replay in (False, True):
+        def make():
+            es = [HeadEngine(n_models=3, feature_dims=dims, eps=[0.1, 1.0, 3.0], seeds=[11, 12, 13], lr=1e-3, init_seed=5),
+                  HeadEngine(n_models=3, feature_dims=dims, eps=[5.0, 8.0, 10.0], seeds=[14, 15, 16], lr=1e-3, init_seed=9)]
+            for e in es:
+                e.fast_replay = replay
+            return es
+        seq, par = make(), make()
+        ens = parallel.StreamedEnsemble(par)
+        for _ in range(6):
+            ref = [e.train_step(blocks, labels) for e in seq]
+            got = ens.train_step(blocks, labels)
+            assert torch.equal(got["loss"], torch.cat([r["loss"] for r in ref]))
+        for _ in range(4):                                   # free-running groups, joined once at the end
+            for e in seq:
+                e.train_step(blocks, labels)
+            ens.train_step(blocks, labels, join=False)
+        ens.join()
+        torch.cuda.synchronize()
+        for a, b in zip(seq, par):
+            assert torch.equal(a.flat, b.flat) and torch.equal(a.DP, b.DP)
+        ev = ens.eval_step(blocks, labels)
+        assert ev["pred"].shape[0] == 6 and ev["logits"].shape[:2] == (6, 8)
