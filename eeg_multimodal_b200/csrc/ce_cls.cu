@@ -251,10 +251,23 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     }
     __syncthreads();
   }
+  const bool direct = a.direct != 0;   // this CTA is the model's only one: its sums ARE the outputs (what the finalize kernel
+                                       // would compute from a single partial row, bit for bit)
   if (threadIdx.x < 4) {
     float s = 0.f;
     for (int w = 0; w < nwarps; ++w) s += s_red[w][threadIdx.x];
-    P[threadIdx.x] = s;
+    if (!direct) {
+      P[threadIdx.x] = s;
+    } else {
+      const int i = threadIdx.x;
+      if (i == 0 && a.stats) a.stats[model * 4 + 0] = s * a.loss_scale;
+      if (i == 1 && a.stats) {
+        a.stats[model * 4 + 1] = s;
+        a.stats[model * 4 + 2] = s * a.loss_scale;
+        a.stats[model * 4 + 3] = static_cast<float>(a.B);
+      }
+      if (MODE == 2 && i >= 2 && a.dbc) a.dbc[model * a.sdbc + (i - 2)] = s;
+    }
   }
   if (MODE == 2) {
     for (int i = threadIdx.x; i < 3 * a.H; i += CE_THREADS) {
@@ -264,7 +277,9 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
       } else {
         for (int w = 0; w < nwarps; ++w) s += s_cs[w * a.H + (i - 2 * a.H)];
       }
-      P[4 + i] = s;
+      if (!direct) P[4 + i] = s;
+      else if (i < 2 * a.H) { if (a.dWc) a.dWc[model * a.sdWc + i] = s; }
+      else if (a.dzsum) a.dzsum[model * a.sdzsum + (i - 2 * a.H)] = s;
     }
   }
 }
@@ -377,6 +392,9 @@ int cls_ce(const CeArgs& a_in, int h_dtype, int dz_dtype, int bwd, int n_models,
   // the weight-side gradients are formed only when the caller asks for one of them
   const int mode = !bwd ? 0 : ((dWc || dbc || dzsum) ? 2 : 1);
   const int ctas = cls_ce_ctas(a.B, n_models);
+  a.direct = ctas == 1;
+  a.loss_scale = loss_scale;
+  a.stats = stats; a.dWc = dWc; a.sdWc = sdWc; a.dbc = dbc; a.sdbc = sdbc; a.dzsum = dzsum; a.sdzsum = sdzsum;
   const int nv = (a.H / 4 + 31) / 32;
   int rc;
   if (nv <= 2) rc = launch_ce<2>(a, h_dtype, dz_dtype, mode, n_models, ctas, s);
@@ -384,6 +402,7 @@ int cls_ce(const CeArgs& a_in, int h_dtype, int dz_dtype, int bwd, int n_models,
   else if (nv <= 6) rc = launch_ce<6>(a, h_dtype, dz_dtype, mode, n_models, ctas, s);
   else rc = launch_ce<8>(a, h_dtype, dz_dtype, mode, n_models, ctas, s);
   if (rc != PGF_OK) return rc;
+  if (a.direct) return PGF_OK;
   const int n = mode == 2 ? 3 * a.H + 4 : 4;
   const dim3 fgrid((n + 31) / 32, n_models);
   cls_ce_finalize_kernel<<<fgrid, 256, 0, s>>>(workspace, ctas, a.H, mode, loss_scale, static_cast<float>(a.B), stats, dWc,

@@ -675,6 +675,10 @@ struct PerturbBwdArgs {
   unsigned long long row0;
   int rows_per_slab;
   float* partial;  // [nslab, D]
+  // nslab == 1 (B <= 32, the reference's batch): the kernel applies the finalize step itself, no second launch
+  const float* coef; long long s_coef;
+  float* dDP; long long s_dDP;
+  int direct, accumulate;
 };
 
 template <typename InT>
@@ -747,6 +751,16 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
     acc.z = fmaf(g.z, l.z, acc.z);
     acc.w = fmaf(g.w, l.w, acc.w);
   }
+  if (a.direct) {   // what perturb_bwd_dp_finalize_kernel computes from a single slab, bit for bit
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    float* o = a.dDP + model * a.s_dDP + col;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (a.coef) v[q] = __fmul_rn(v[q], a.coef[model * a.s_coef + col + q]);
+      o[q] = a.accumulate ? __fadd_rn(o[q], v[q]) : v[q];
+    }
+    return;
+  }
   *reinterpret_cast<float4*>(a.partial + (static_cast<long long>(model) * a.nslab + slab) * a.D + col) = acc;
 }
 
@@ -779,9 +793,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) perturb_bwd_dp_finalize_kernel
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < FIN_WARPS; ++w) s += s_part[w][lane];
-    const float v = coef ? s * coef[model * s_coef + d] : s;
-    float* o = dDP + model * s_dDP + d;
-    *o = accumulate != 0.f ? *o + v : v;
+    const float v = coef ? __fmul_rn(s, coef[model * s_coef + d]) : s;   // explicit roundings: the single-slab path of
+    float* o = dDP + model * s_dDP + d;                                   // perturb_bwd_dp_kernel must match bit for bit
+    *o = accumulate != 0.f ? __fadd_rn(*o, v) : v;
   }
 }
 
@@ -827,6 +841,8 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
   a.row0 = row0;
   a.rows_per_slab = (B + slabs - 1) / slabs;
   a.partial = workspace;
+  a.direct = slabs == 1;
+  a.coef = coef; a.s_coef = s_coef; a.dDP = dDP; a.s_dDP = s_dDP; a.accumulate = accumulate;
   const dim3 grid((D / 4 + 127) / 128, slabs, n_models);
   a.rk = philox_make_keys(seed);
   if (noise == PGF_NOISE_INJECTED) {
@@ -846,6 +862,7 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
       perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
+  if (a.direct) return PGF_OK;
   const dim3 fgrid((D + 31) / 32, n_models);
   perturb_bwd_dp_finalize_kernel<<<fgrid, FIN_WARPS * 32, 0, s>>>(workspace, slabs, D, coef, s_coef, dDP, s_dDP, accumulate ? 1.f : 0.f);
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp(finalize)");

@@ -141,7 +141,7 @@ class CallPlan:
                     if not (isinstance(x, int) and isinstance(y, int)) or (y - x) % steps_apart:
                         raise RuntimeError(f"{name}: argument {i} changed between steps in a way a plan cannot replay ({x} -> {y})")
                     dyn.append((i, (y - x) // steps_apart, 0xFFFFFFFF if types[i] is L.U32 else 0xFFFFFFFFFFFFFFFF))
-            self.calls.append((tag, name, getattr(lib, name), list(a), dyn, sub, L.LAUNCHES_PER_CALL.get(name, 1)))
+            self.calls.append((tag, name, getattr(lib, name), list(a), dyn, sub, L.launches_of(name, a)))
         self.n_launches = sum(c[6] for c in self.calls)
         self.ws_generation = WS_GENERATION   # the plan is void once any scratch buffer it may point into has moved
 
