@@ -85,6 +85,7 @@ class HeadEngine:
         self.noise_offset = 0
         self._bufs = {}
         self._injected = None
+        self._coef_key = None
         self.exp_eps_dev = torch.tensor(self.exp_eps, dtype=torch.float32, device=dev)
         # arbitrary per-model seeds: a device array read by the grouped kernels (one launch for the whole sweep)
         self.seeds_dev = torch.tensor([s if s < 2 ** 63 else s - 2 ** 64 for s in self.seeds], dtype=torch.int64, device=dev)
@@ -155,6 +156,11 @@ class HeadEngine:
             t = self._bufs[key] = torch.empty(shape, dtype=dtype, device=self.device)
         return t
 
+    def _coef_state(self):
+        """What the cached (w, eps_hat, d eps_hat/d DP) rows depend on: DP as torch sees it (`_version` counts in-place
+        writes: load_state_dict, user code), DP as the Adam kernel moves it (t_dp), and e^eps / the formula switch."""
+        return (self.DP._version, self.t_dp, self.exp_eps_dev.data_ptr(), self.exp_eps_dev._version, self.fixed)
+
     def inject_noise(self, lap, gum=None):
         """Per-model injected noise for the NEXT pass: lap [M,B,D], gum [M,2,B,D] (parity tests)."""
         self._injected = (lap.contiguous(), None if gum is None else gum.contiguous())
@@ -163,7 +169,10 @@ class HeadEngine:
         """kernel (a) for every model; returns the per-model coefficient rows and the noise spec."""
         M, D = self.M, self.D
         coef = self._buf("coef", (3, M, D), torch.float32)
-        ops.dp_coeffs(self.DP, self.exp_eps_dev, self.fixed, out=coef)
+        key = self._coef_state()
+        if self._coef_key != key:      # DP only moves in the DP pass (past_acc.py:203): one dp_coeffs per step, not two
+            ops.dp_coeffs(self.DP, self.exp_eps_dev, self.fixed, out=coef)
+            self._coef_key = key
         inj = self._injected
         self._injected = None
         offset = self.noise_offset
@@ -334,7 +343,8 @@ class HeadEngine:
             n, rem = divmod(self.t_model - ent["state"][2], 1)
             d = ent["dstate"]
             ok = (self.noise_offset == ent["state"][0] + n * d[0] and self.t_dp == ent["state"][1] + n * d[1]
-                  and row0 == ent["row0"] + n * ent["drow0"] and ent["plan"].ws_generation == ops.WS_GENERATION)
+                  and row0 == ent["row0"] + n * ent["drow0"] and ent["plan"].ws_generation == ops.WS_GENERATION
+                  and self._coef_key == self._coef_state())   # the plan skips pass 1's dp_coeffs: the cached rows must be current
             if ok:
                 hook = None
                 if grad_hook is not None:
@@ -343,6 +353,7 @@ class HeadEngine:
                 self.noise_offset += d[0]
                 self.t_dp += d[1]
                 self.t_model += d[2]
+                self._coef_key = self._coef_state()      # the replayed pass 2 recomputed the rows after the DP update
                 return self._result(ent["stats"])
             self._plans.pop(key)          # the step state no longer advances the way it did while recording
             ent = None
