@@ -175,3 +175,16 @@ def test_call_plan_logic_with_a_stub_library(monkeypatch):
         ops.CallPlan([adam(100, 5)], [adam(100, 6)[:2] + ((100, 201, 300, 400, None, 1000, 6, 1e-3, 0.9, 0.999, 1e-8, 1.0, 77),)], {})
     with pytest.raises(RuntimeError, match="different call sequences"):
         ops.CallPlan([fill], [fill, fill], {})
+
+
+def test_launch_accounting_follows_the_single_launch_paths():
+    """bench.py's `gpu_launches` is a claim: pgf_cls_ce (B <= 8) and pgf_perturb_gate_bwd_dp (B <= 32) finish in their
+    main kernel, everything else as tabulated."""
+    from eeg_multimodal_b200 import _lib
+
+    ce = [0] * len(_lib.SIGNATURES["pgf_cls_ce"][1])
+    bw = [0] * len(_lib.SIGNATURES["pgf_perturb_gate_bwd_dp"][1])
+    for B, n_ce, n_bw in ((1, 1, 1), (8, 1, 1), (9, 2, 1), (32, 2, 1), (33, 2, 2), (65536, 2, 2)):
+        ce[10], bw[4] = B, B
+        assert _lib.launches_of("pgf_cls_ce", ce) == n_ce and _lib.launches_of("pgf_perturb_gate_bwd_dp", bw) == n_bw
+    assert _lib.launches_of("pgf_gemm_bf16_ddp", ()) == 2 and _lib.launches_of("pgf_adam_step", ()) == 1
