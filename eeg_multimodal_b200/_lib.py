@@ -51,6 +51,30 @@ SIGNATURES = {
     "pgf_prigumbel_bwd": (I, [P, LL, P, P, LL, P, F, F, P, LL, P, I, I, I, P, SZ, P]),
 }
 
+
+
+class SweepDesc(C.Structure):
+    """pgf_sweep_desc (include/pgfuse.h), field for field."""
+    _fields_ = [(n, I) for n in ("n_models", "B", "d0", "d1", "d2", "H", "dp_pass", "fixed_formula", "use_pdl", "reserved_")] + \
+               [(n, F) for n in ("tau", "lr", "beta1", "beta2", "adam_eps", "reserved_f_")] + \
+               [("x0", P), ("ld0", LL), ("x1", P), ("ld1", LL), ("x2", P), ("ld2", LL), ("labels", P), ("src_rows", P), ("n_rows", LL),
+                ("params", P), ("adam_m", P), ("adam_v", P), ("grads", P), ("P", LL)] + \
+               [(n, LL) for n in ("off_W1", "off_b1", "off_W2", "off_b2", "off_Wc", "off_bc")] + \
+               [("DP", P), ("DP_m", P), ("DP_v", P), ("dDP", P), ("coef", P), ("exp_eps", P), ("seeds", P), ("row0", U64),
+                ("stats_dp", P), ("stats_model", P), ("logits", P), ("pred", P), ("state", P), ("workspace", P), ("workspace_bytes", SZ)]
+
+
+SIGNATURES.update({
+    "pgf_step_state_set": (I, [P, LL, LL, LL, LL, F, F, F, P]),
+    "pgf_sweep_plan_workspace": (SZ, [I, I, I, I]),
+    "pgf_sweep_plan_create": (I, [C.POINTER(SweepDesc), C.POINTER(P)]),
+    "pgf_sweep_plan_reset": (I, [P, P]),
+    "pgf_sweep_plan_capture": (I, [P, P, I]),
+    "pgf_sweep_plan_run": (I, [P, P, I]),
+    "pgf_sweep_plan_launches_per_step": (I, [P]),
+    "pgf_sweep_plan_destroy": (I, [P]),
+})
+
 _lib = None
 
 

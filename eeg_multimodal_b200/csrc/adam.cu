@@ -49,16 +49,6 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-AdamCoef make_adam_coef(int step, float lr, float b1, float b2, float eps, float grad_scale) {
-  const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
-  AdamCoef c;
-  c.b1 = b1; c.b2 = b2; c.eps = eps; c.grad_scale = grad_scale;
-  c.step_size = lr / static_cast<float>(bc1);
-  c.bc2_sqrt = static_cast<float>(sqrt(bc2));
-  return c;
-}
-
 int adam_step(float* p, const float* g, float* m, float* v, void* shadow, long long n, int step, float lr, float b1,
               float b2, float eps, float grad_scale, cudaStream_t s, long long model_stride, int n_models) {
   if (n <= 0 || n_models <= 0) return PGF_OK;

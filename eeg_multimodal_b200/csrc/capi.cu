@@ -74,6 +74,11 @@ int cached_occupancy(const void* kernel, int threads, size_t smem, int fallback)
   return occ;
 }
 
+static thread_local bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+PdlScope::PdlScope(bool on) : prev(g_pdl) { g_pdl = on; }
+PdlScope::~PdlScope() { g_pdl = prev; }
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace pgf
@@ -117,7 +122,8 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   bool gate = want_gate != 0 && noise_mode != PGF_NOISE_NONE;
   if (noise_mode == PGF_NOISE_INJECTED && !gum) gate = false;
   PGF_CHECK_ARG(tau > 0.f, "pgf_perturb_gate_fwd: tau must be > 0");
-  PerturbFwdArgs a;
+  PerturbFwdArgs a = {};
+  a.n_rep = 1;
   a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
   a.ld[0] = ld0; a.ld[1] = ld1; a.ld[2] = ld2;
   a.sx[0] = sx0; a.sx[1] = sx1; a.sx[2] = sx2;
@@ -286,7 +292,7 @@ int pgf_cls_ce(const void* h, int h_dtype, long long ldh, long long sh, const fl
   PGF_CHECK_ARG(aligned16(h) && aligned16(Wc) && (ldh % 4) == 0 && (sWc % 4) == 0 && (sh % 4) == 0,
                 "pgf_cls_ce: h, Wc must be 16-byte aligned");
   if (backward && dz) PGF_CHECK_ARG(aligned16(dz) && (lddz % 4) == 0 && (sdz % 4) == 0, "pgf_cls_ce: dz must be 16-byte aligned");
-  CeArgs a;
+  CeArgs a = {};
   a.h = h; a.ldh = ldh; a.sh = sh; a.Wc = Wc; a.sWc = sWc; a.bc = bc; a.sbc = sbc; a.labels = labels; a.slab = slabels;
   a.logits = logits; a.slogits = slogits; a.pred = pred; a.spred = spred; a.dz = dz; a.lddz = lddz; a.sdz = sdz;
   a.partial = workspace; a.B = B; a.H = H; a.grad_scale = grad_scale; a.through_tanh = through_tanh;
@@ -324,9 +330,11 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
                     aligned16(mW) && aligned16(vW),
                 "pgf_linear_adam_step: K, ldx, strides must be multiples of 4 and X, W, mW, vW 16-byte aligned");
   PGF_CHECK_ARG(!bias || (mb && vb), "pgf_linear_adam_step: bias needs its moment buffers");
-  LinAdamArgs a;
-  a.dY = dY; a.ldy = ldy; a.sdY = sdY; a.X = X; a.ldx = ldx; a.sX = sX; a.W = W; a.mW = mW; a.vW = vW;
-  a.bias = bias; a.mb = mb; a.vb = vb; a.sP = sP; a.B = B; a.N = N; a.K = K; a.rows_per_cta = 0;
+  LinAdamArgs a = {};
+  LinAdamLayer& l = a.l[0];
+  l.dY = dY; l.ldy = ldy; l.sdY = sdY; l.X = X; l.ldx = ldx; l.sX = sX; l.W = W; l.mW = mW; l.vW = vW;
+  l.bias = bias; l.mb = mb; l.vb = vb; l.N = N; l.K = K;
+  a.n_layers = 1; a.sP = sP; a.B = B; a.st = nullptr; a.adv = StepAdvance{};
   a.c = make_adam_coef(step, lr, beta1, beta2, eps, grad_scale);
   return linear_adam_step(a, n_models, static_cast<cudaStream_t>(stream));
 }

@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     }
     __syncthreads();
   }
+  griddep_wait();     // Wc above never comes from the preceding kernel of a step; the activations below do
+  griddep_launch();
+  const long long cursor = (a.st && a.gather) ? a.st->cursor : 0;
   // MODE 2 accumulators: dWc rows in registers, the dz column sums in the warp's own shared-memory row
   float4 dw0[MODE == 2 ? NV : 1], dw1[MODE == 2 ? NV : 1];
   float* s_dsum = s_cs + warp * a.H;
@@ -180,7 +183,8 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     }
     z0 = warp_sum(z0) + b0;
     z1 = warp_sum(z1) + b1;
-    const int label = labels ? static_cast<int>(labels[row]) : 0;
+    const long long lrow = a.gather ? (a.src_rows ? a.src_rows[cursor + row] : cursor + row) : row;
+    const int label = labels ? static_cast<int>(labels[lrow]) : 0;
     const float m = fmaxf(z0, z1);
     const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
     const float loss = lse - (label == 0 ? z0 : z1);
@@ -267,6 +271,13 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
         a.stats[model * 4 + 3] = static_cast<float>(a.B);
       }
       if (MODE == 2 && i >= 2 && a.dbc) a.dbc[model * a.sdbc + (i - 2)] = s;
+      if (MODE == 2 && i >= 2 && a.adam_mb) {   // fused model_optimizer.step() on classifier.bias
+        const AdamCoef c = adam_coef_at(a.adam_c, a.st, 1);
+        const long long o = model * a.sbc + (i - 2);
+        float p = const_cast<float*>(a.bc)[o], m = a.adam_mb[o], v = a.adam_vb[o];
+        adam_update(p, m, v, s, c);
+        const_cast<float*>(a.bc)[o] = p; a.adam_mb[o] = m; a.adam_vb[o] = v;
+      }
     }
   }
   if (MODE == 2) {
@@ -278,7 +289,16 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
         for (int w = 0; w < nwarps; ++w) s += s_cs[w * a.H + (i - 2 * a.H)];
       }
       if (!direct) P[4 + i] = s;
-      else if (i < 2 * a.H) { if (a.dWc) a.dWc[model * a.sdWc + i] = s; }
+      else if (i < 2 * a.H) {
+        if (a.dWc) a.dWc[model * a.sdWc + i] = s;
+        if (a.adam_m) {   // fused model_optimizer.step() on classifier.weight (every row read its copy in shared memory)
+          const AdamCoef c = adam_coef_at(a.adam_c, a.st, 1);
+          const long long o = model * a.sWc + i;
+          float p = const_cast<float*>(a.Wc)[o], m = a.adam_m[o], v = a.adam_v[o];
+          adam_update(p, m, v, s, c);
+          const_cast<float*>(a.Wc)[o] = p; a.adam_m[o] = m; a.adam_v[o] = v;
+        }
+      }
       else if (a.dzsum) a.dzsum[model * a.sdzsum + (i - 2 * a.H)] = s;
     }
   }
@@ -351,7 +371,7 @@ static int launch_ce(const CeArgs& a, int h_dtype, int dz_dtype, int mode, int n
 #define PGF_CE_LAUNCH(HT, DT, MD)                                                                        \
   do {                                                                                                   \
     ensure_dynamic_smem(reinterpret_cast<const void*>(cls_ce_kernel<NV, HT, DT, MD>), smem);              \
-    cls_ce_kernel<NV, HT, DT, MD><<<grid, block, smem, s>>>(a);                                          \
+    launch(cls_ce_kernel<NV, HT, DT, MD>, grid, block, smem, s, a);                                      \
   } while (0)
 #define PGF_CE_MODES(HT, DT)                         \
   do {                                               \
@@ -393,6 +413,10 @@ int cls_ce(const CeArgs& a_in, int h_dtype, int dz_dtype, int bwd, int n_models,
   const int mode = !bwd ? 0 : ((dWc || dbc || dzsum) ? 2 : 1);
   const int ctas = cls_ce_ctas(a.B, n_models);
   a.direct = ctas == 1;
+  if ((a.adam_m || a.adam_mb) && !(a.direct && mode == 2)) {
+    set_error("pgf_cls_ce: the fused classifier Adam needs the one-CTA-per-model pass-2 launch (B <= 8)");
+    return PGF_ERR_UNSUPPORTED;
+  }
   a.loss_scale = loss_scale;
   a.stats = stats; a.dWc = dWc; a.sdWc = sdWc; a.dbc = dbc; a.sdbc = sdbc; a.dzsum = dzsum; a.sdzsum = sdzsum;
   const int nv = (a.H / 4 + 31) / 32;

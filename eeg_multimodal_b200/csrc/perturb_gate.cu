@@ -61,6 +61,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
   const int model = blockIdx.y;
   const int nvec = a.D >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  griddep_wait();     // the coefficient rows (and, in a step chain, DP) come from the preceding kernel
+  griddep_launch();
+  const unsigned int offset0 = a.offset + (a.st ? static_cast<unsigned int>(a.st->noise_offset) : 0u);
+  const long long cursor = (a.st && a.gather) ? a.st->cursor : 0;
+  const int n_rep = a.n_rep > 1 ? a.n_rep : 1;
   if (NOISE != PGF_NOISE_NONE) {
     const float4* ge = reinterpret_cast<const float4*>(a.eps_hat + model * a.s_coef);
     const float4* gw = reinterpret_cast<const float4*>(a.w + model * a.s_coef);
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
   const float* x2 = a.d[2] ? a.x[2] + model * a.sx[2] : nullptr;
   const unsigned long long seed = a.model_seeds ? a.model_seeds[model] : a.seed + static_cast<unsigned long long>(model) * a.seed_step;
   const unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
-  const long long BD = static_cast<long long>(a.B) * a.D;
+  const long long BD = static_cast<long long>(a.B) * n_rep * a.D;
   const float* lap = a.lap ? a.lap + model * BD : nullptr;
   const float* gum = a.gum ? a.gum + model * 2 * BD : nullptr;
   unsigned char* gate_idx = a.gate_idx ? a.gate_idx + model * BD : nullptr;
@@ -101,14 +106,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
   }
 
   int it = 0;
-  for (long long row = blockIdx.x; row < a.B; row += gridDim.x, ++it) {
+  const long long vrows = static_cast<long long>(a.B) * n_rep;
+  for (long long row = blockIdx.x; row < vrows; row += gridDim.x, ++it) {
+    // virtual row = (repetition, batch row); the batch row may be gathered from a resident dataset
+    const int rep = static_cast<int>(row / a.B);
+    const long long brow = row - static_cast<long long>(rep) * a.B;
+    const long long srow = a.gather ? (a.src_rows ? a.src_rows[cursor + brow] : cursor + brow) : brow;
+    const unsigned int offs = offset0 + static_cast<unsigned int>(rep);
     float4 v[NV];
     float mn = INFINITY, mx = -INFINITY, probe = 0.f;
     // all loads of the row are issued before first use
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int col = (tid + FWD_THREADS * k) << 2;
-      if (col < a.D) v[k] = ldg_stream(reinterpret_cast<const float4*>(pk[k] + row * ldk[k]));
+      if (col < a.D) v[k] = ldg_stream(reinterpret_cast<const float4*>(pk[k] + srow * ldk[k]));
     }
     // ---- row min / max (models.py:70-71).  torch.min/max propagate NaN while fminf/fmaxf drop it, so
     // a running sum is carried as a NaN probe (NaN in -> NaN out; an inf/-inf mix also gives the NaN
@@ -142,10 +153,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
     const float range = __fsub_rn(mx, mn);
     const float inv_range = __frcp_rn(range);
     if (tid == 0) {
-      if (a.row_min) a.row_min[model * a.B + row] = mn;
-      if (a.row_max) a.row_max[model * a.B + row] = mx;
+      if (a.row_min) a.row_min[model * vrows + row] = mn;
+      if (a.row_max) a.row_max[model * vrows + row] = mx;
     }
-    const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(row));
+    const unsigned int grow = static_cast<unsigned int>(a.row0 + static_cast<unsigned long long>(brow));
     char* outp = static_cast<char*>(a.out) + model * a.s_out * static_cast<long long>(sizeof(OutT));
 
 #pragma unroll
@@ -183,8 +194,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
         } else if (NOISE == PGF_NOISE_PHILOX) {
           const float4 e4 = s_eps[j];
           const float eh[4] = {e4.x, e4.y, e4.z, e4.w};  // = -ln2 * eps_hat
-          const uint4 r = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, a.rk)
-                                    : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, a.offset, k0, k1);
+          const uint4 r = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, offs, a.rk)
+                                    : philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_LAPLACE, offs, k0, k1);
           const unsigned int rb[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) f[e] = perturb_fma(f[e], rb[e], eh[e]);
@@ -193,8 +204,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 6) perturb_gate_fwd_kernel(const 
             // value IS the perturbed value; only the gate index is a real output.
             const float4 w4 = s_w[j];
             const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-            const uint4 q0 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL0, a.offset, k0, k1);
-            const uint4 q1 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL1, a.offset, k0, k1);
+            const uint4 q0 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL0, offs, k0, k1);
+            const uint4 q1 = philox4x32_10(static_cast<unsigned int>(j), grow, PGF_STREAM_GUMBEL1, offs, k0, k1);
             const unsigned int qa[4] = {q0.x, q0.y, q0.z, q0.w}, qb[4] = {q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -578,8 +589,8 @@ static int launch_fwd_gate(const PerturbFwdArgs& a, bool want_gate, cudaStream_t
 #define PGF_FWD_LAUNCH(GATE, CK)                                                                                  \
   do {                                                                                                            \
     auto kern = perturb_gate_fwd_kernel<NV, NOISE, OutT, GATE, CK>;                                               \
-    const dim3 grid(persistent_grid(kern, FWD_THREADS, smem, a.n_models, a.B), a.n_models);                       \
-    kern<<<grid, FWD_THREADS, smem, stream>>>(a);                                                                 \
+    const dim3 grid(persistent_grid(kern, FWD_THREADS, smem, a.n_models, a.B * (a.n_rep > 1 ? a.n_rep : 1)), a.n_models); \
+    launch(kern, grid, dim3(FWD_THREADS), smem, stream, a);                                                       \
   } while (0)
   if (want_gate) PGF_FWD_LAUNCH(true, false);
   else if (constkeys) PGF_FWD_LAUNCH(false, (NOISE == PGF_NOISE_PHILOX));
@@ -605,7 +616,8 @@ static int launch_fwd_nv(const PerturbFwdArgs& a, int noise, int out_dtype, bool
 static int perturb_gate_fwd_one(const PerturbFwdArgs& a, int noise, int out_dtype, bool want_gate, cudaStream_t s) {
   const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
   static const bool no_ring = getenv("PGF_PERTURB_NO_RING") != nullptr;
-  if (!no_ring && noise != PGF_NOISE_INJECTED && !want_gate && a.n_models == 1 && static_cast<long long>(a.B) * a.D >= (1LL << 22)) {
+  if (!no_ring && noise != PGF_NOISE_INJECTED && !want_gate && a.n_models == 1 && !a.st && !a.gather && a.n_rep <= 1 &&
+      static_cast<long long>(a.B) * a.D >= (1LL << 22)) {
     if (nv <= 2) return launch_fwd_ring_nv<2>(a, noise, out_dtype, s);
     if (nv <= 5) return launch_fwd_ring_nv<5>(a, noise, out_dtype, s);
     if (nv <= 8) return launch_fwd_ring_nv<8>(a, noise, out_dtype, s);
@@ -624,6 +636,7 @@ int perturb_gate_fwd(const PerturbFwdArgs& a_in, int noise, int out_dtype, bool 
   // arguments (constant-bank operands).  Small batches (the B=8 sweep): one grouped launch.
   const bool big = static_cast<long long>(a.B) * a.D >= (1LL << 22);
   static const bool no_ring = getenv("PGF_PERTURB_NO_RING") != nullptr;
+  if (a.st || a.gather || a.n_rep > 1) return perturb_gate_fwd_one(a, noise, out_dtype, want_gate, s);
   if (!no_ring && noise == PGF_NOISE_PHILOX && a.n_models > 1 && !want_gate && big && a.sx[0] == 0 && a.sx[1] == 0 && a.sx[2] == 0) {
     // one batch shared by the whole sweep: fetch / normalise each row once, perturb it once per model
     const int nv = (a.D / 4 + FWD_THREADS - 1) / FWD_THREADS;
@@ -679,7 +692,21 @@ struct PerturbBwdArgs {
   const float* coef; long long s_coef;
   float* dDP; long long s_dDP;
   int direct, accumulate;
+  const StepState* st;      // offset += st->noise_offset; Adam coefficients of the DP group
+  int fused;                // direct mode only: Adam(DP) + coefficient refresh in the same thread (DpAdamFuse)
+  DpAdamFuse f;
 };
+
+// (w, eps_hat, d eps_hat/d DP) of one column: the arithmetic of dp_coeffs_kernel, shared with the fused DP-pass tail
+__device__ __forceinline__ void dp_coeff_one(float x, float exp_eps, int fixed, float& w, float& eh, float& de) {
+  w = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  const float num = __fsub_rn(exp_eps, w);
+  const float ratio = __fdiv_rn(num, __fsub_rn(1.0f, w));
+  const float L = logf(ratio);
+  eh = fixed ? __fdiv_rn(1.0f, L) : L;
+  const float t = __fdiv_rn(__fmul_rn(__fsub_rn(exp_eps, 1.0f), w), num);
+  de = fixed ? __fdiv_rn(-t, __fmul_rn(L, L)) : t;
+}
 
 template <typename InT>
 __device__ __forceinline__ float4 load_in4(const void* p, long long off);
@@ -698,7 +725,10 @@ template <int NOISE, typename InT, bool CONSTKEYS>
 __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // float4 column index
   const int col = j << 2;
+  griddep_wait();
+  griddep_launch();
   if (col >= a.D) return;
+  const unsigned int offs = a.offset + (a.st ? static_cast<unsigned int>(a.st->noise_offset) : 0u);
   const int slab = blockIdx.y, model = blockIdx.z;
   const int r0 = slab * a.rows_per_slab;
   const int r1 = min(a.B, r0 + a.rows_per_slab);
@@ -719,9 +749,9 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
         l[u] = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r + u) * a.D + col));
       } else {
         const uint4 q = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
-                                                     PGF_STREAM_LAPLACE, a.offset, a.rk)
+                                                     PGF_STREAM_LAPLACE, offs, a.rk)
                                  : philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r + u),
-                                                 PGF_STREAM_LAPLACE, a.offset, k0, k1);
+                                                 PGF_STREAM_LAPLACE, offs, k0, k1);
         l[u] = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z),
                            laplace_from_bits(q.w));
       }
@@ -741,9 +771,9 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
       l = ldg_stream(reinterpret_cast<const float4*>(lapm + static_cast<long long>(r) * a.D + col));
     } else {
       const uint4 q = CONSTKEYS ? philox4x32_10_rk(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
-                                                   PGF_STREAM_LAPLACE, a.offset, a.rk)
+                                                   PGF_STREAM_LAPLACE, offs, a.rk)
                                : philox4x32_10(static_cast<unsigned int>(j), static_cast<unsigned int>(a.row0 + r),
-                                               PGF_STREAM_LAPLACE, a.offset, k0, k1);
+                                               PGF_STREAM_LAPLACE, offs, k0, k1);
       l = make_float4(laplace_from_bits(q.x), laplace_from_bits(q.y), laplace_from_bits(q.z), laplace_from_bits(q.w));
     }
     acc.x = fmaf(g.x, l.x, acc.x);
@@ -757,7 +787,23 @@ __global__ void __launch_bounds__(128) perturb_bwd_dp_kernel(const PerturbBwdArg
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (a.coef) v[q] = __fmul_rn(v[q], a.coef[model * a.s_coef + col + q]);
-      o[q] = a.accumulate ? __fadd_rn(o[q], v[q]) : v[q];
+      v[q] = a.accumulate ? __fadd_rn(o[q], v[q]) : v[q];
+      o[q] = v[q];
+    }
+    if (a.fused) {   // DP_optimizer.step() (past_acc.py:203) and the coefficient rows the next forward reads
+      const AdamCoef c = adam_coef_at(a.f.c, a.st, 0);
+      const long long i = static_cast<long long>(model) * a.D + col;
+      const float ee = a.f.exp_eps[model];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float p = a.f.DP[i + q], m = a.f.DP_m[i + q], vv = a.f.DP_v[i + q];
+        adam_update(p, m, vv, v[q], c);
+        a.f.DP[i + q] = p; a.f.DP_m[i + q] = m; a.f.DP_v[i + q] = vv;
+        float w, eh, de;
+        dp_coeff_one(p, ee, a.f.fixed, w, eh, de);
+        const long long ci = model * a.s_coef + col + q;
+        a.f.w[ci] = w; a.f.eps_hat[ci] = eh; a.f.deps[ci] = de;
+      }
     }
     return;
   }
@@ -819,8 +865,12 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
                         const float* lap, unsigned long long seed, unsigned long long seed_step,
                         const unsigned long long* model_seeds, unsigned int offset, unsigned long long row0, const float* coef,
                         long long s_coef, float* workspace, size_t workspace_bytes, float* dDP, long long s_dDP, int accumulate,
-                        cudaStream_t s) {
+                        cudaStream_t s, const StepState* st, const DpAdamFuse* fuse) {
   const int slabs = perturb_bwd_slabs(B, D, n_models);
+  if (fuse && slabs != 1) {
+    set_error("pgf_perturb_gate_bwd_dp: the fused Adam(DP) tail needs a single-slab launch (B <= 32), got B=%d", B);
+    return PGF_ERR_UNSUPPORTED;
+  }
   const size_t need = static_cast<size_t>(n_models) * slabs * D * sizeof(float);
   if (workspace_bytes < need) {
     set_error("pgf_perturb_gate_bwd_dp: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -843,23 +893,25 @@ int perturb_gate_bwd_dp(const void* dF, int dtype, long long ld, long long s_dF,
   a.partial = workspace;
   a.direct = slabs == 1;
   a.coef = coef; a.s_coef = s_coef; a.dDP = dDP; a.s_dDP = s_dDP; a.accumulate = accumulate;
+  a.st = st; a.fused = fuse != nullptr;
+  if (fuse) a.f = *fuse; else a.f = DpAdamFuse{};
   const dim3 grid((D / 4 + 127) / 128, slabs, n_models);
   a.rk = philox_make_keys(seed);
   if (noise == PGF_NOISE_INJECTED) {
     if (dtype == PGF_DT_F32)
-      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float, false><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, float, false>, grid, dim3(128), 0, s, a);
     else
-      perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_INJECTED, __nv_bfloat16, false>, grid, dim3(128), 0, s, a);
   } else if (n_models == 1 && !model_seeds) {
     if (dtype == PGF_DT_F32)
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, true><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, true>, grid, dim3(128), 0, s, a);
     else
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, true><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, true>, grid, dim3(128), 0, s, a);
   } else {
     if (dtype == PGF_DT_F32)
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, false><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, float, false>, grid, dim3(128), 0, s, a);
     else
-      perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, false><<<grid, 128, 0, s>>>(a);
+      launch(perturb_bwd_dp_kernel<PGF_NOISE_PHILOX, __nv_bfloat16, false>, grid, dim3(128), 0, s, a);
   }
   PGF_CUDA_LAUNCH_CHECK("pgf_perturb_gate_bwd_dp");
   if (a.direct) return PGF_OK;
@@ -881,18 +933,11 @@ __global__ void dp_coeffs_kernel(const float* __restrict__ DP, const float* __re
   const int model = blockIdx.y;
   if (d >= D) return;
   const long long i = static_cast<long long>(model) * D + d;
-  const float exp_eps = exp_eps_arr[model];
-  const float x = DP[i];
-  const float w = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-  const float num = __fsub_rn(exp_eps, w);
-  const float ratio = __fdiv_rn(num, __fsub_rn(1.0f, w));
-  const float L = logf(ratio);
+  float w, eh, de;
+  dp_coeff_one(DP[i], exp_eps_arr[model], fixed, w, eh, de);
   if (w_out) w_out[i] = w;
-  if (eps_hat) eps_hat[i] = fixed ? __fdiv_rn(1.0f, L) : L;
-  if (deps) {
-    const float t = (exp_eps - 1.0f) * w / num;
-    deps[i] = fixed ? -t / (L * L) : t;
-  }
+  if (eps_hat) eps_hat[i] = eh;
+  if (deps) deps[i] = de;
 }
 
 int dp_coeffs(const float* DP, const float* exp_eps, int fixed, int D, int n_models, float* w, float* eps_hat, float* deps,

@@ -59,6 +59,56 @@ int num_sms();
 void ensure_dynamic_smem(const void* kernel, size_t smem);
 int cached_occupancy(const void* kernel, int threads, size_t smem, int fallback);
 
+// ---- programmatic dependent launch (the fused B<=8 sweep step, sweep_step.cu) ---------------------------------------
+// Every kernel of that chain is written as  [prologue that touches nothing its predecessor writes]  griddep_wait()
+// griddep_launch()  [body].  Launched with the stream-serialization attribute (pdl_scope active) the next kernel's CTAs
+// become resident while the predecessor's last wave drains, run their prologue (weight prefetch, Philox bits, smem
+// carve-up) and block in griddep_wait() until the predecessor has completed and flushed.  launch_dependents is issued
+// only AFTER the kernel's own wait, so completion is transitive: a prologue may read anything except what the
+// IMMEDIATE predecessor writes.  Without the attribute both instructions are no-ops (ordinary stream order).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// thread-local switch read by launch(): set by the sweep-step plan while it enqueues its chain
+bool pdl_enabled();
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on);
+  ~PdlScope();
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Device-resident step state of a training loop (one per engine / plan): what changes from step to step lives here
+// instead of in kernel arguments, so a whole step is a constant launch sequence (CUDA graph, no host in the loop).
+// Kernels ADD these to their ordinary arguments (NULL state = plain arguments).  Written only by step_state_set /
+// step_advance (sweep_step.cu); the Adam coefficients are those of step t+1, i.e. of the NEXT update.
+struct StepState {
+  long long noise_offset;   // + Philox offset argument
+  long long t_dp;           // Adam steps already taken by the DP group
+  long long t_model;        // ... by the weight group
+  long long cursor;         // position of the current batch in the resident dataset / permutation
+  float dp_step_size, dp_bc2_sqrt;        // lr/(1-b1^t), sqrt(1-b2^t) at t = t_dp + 1
+  float model_step_size, model_bc2_sqrt;  // same at t = t_model + 1
+  float lr, b1, b2, pad;                  // what step_advance needs to form the next coefficients
+};
+static_assert(sizeof(StepState) == 64, "StepState is part of the C ABI (pgf_step_state_*): 64 bytes");
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

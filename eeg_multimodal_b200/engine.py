@@ -165,14 +165,19 @@ class HeadEngine:
         """Per-model injected noise for the NEXT pass: lap [M,B,D], gum [M,2,B,D] (parity tests)."""
         self._injected = (lap.contiguous(), None if gum is None else gum.contiguous())
 
-    def _perturb(self, blocks, hard, out, row0):
-        """kernel (a) for every model; returns the per-model coefficient rows and the noise spec."""
-        M, D = self.M, self.D
-        coef = self._buf("coef", (3, M, D), torch.float32)
+    def _ensure_coef(self):
+        """The cached (w, eps_hat, d eps_hat/d DP) rows [3,M,D], recomputed only when DP moved."""
+        coef = self._buf("coef", (3, self.M, self.D), torch.float32)
         key = self._coef_state()
         if self._coef_key != key:      # DP only moves in the DP pass (past_acc.py:203): one dp_coeffs per step, not two
             ops.dp_coeffs(self.DP, self.exp_eps_dev, self.fixed, out=coef)
             self._coef_key = key
+        return coef
+
+    def _perturb(self, blocks, hard, out, row0):
+        """kernel (a) for every model; returns the per-model coefficient rows and the noise spec."""
+        M, D = self.M, self.D
+        coef = self._ensure_coef()
         inj = self._injected
         self._injected = None
         offset = self.noise_offset

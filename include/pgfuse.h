@@ -230,6 +230,62 @@ int pgf_prigumbel_bwd(const float* z, long long ldz, const float* coef, const fl
                       const float* wloss, float exp_eps, float wloss_scale, float* dz, long long ld_dz, float* dw,
                       int accumulate, int B, int H, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (a12, f1, f3) the whole reference step at the reference batch size, one constant launch sequence ------------
+ * replaces: one iteration of the training loop past_acc.py:198-212 (== base_train.py:183-210) for EVERY model of a
+ *           sweep -- pass 1 (hard=False) forward / cal_loss / backward / DP_optimizer.step(), pass 2 (hard=True)
+ *           forward / cal_loss / backward / model_optimizer.step() -- plus the shuffled DataLoader fetch in front of it
+ *           (data.py:37-45): the batch is rows src_rows[cursor .. cursor+B) of feature blocks resident in HBM.
+ * Everything that changes between steps lives in a 64-byte DEVICE struct (pgf_step_state: Philox offset, Adam step
+ * counts and bias corrections, batch cursor) that the kernels add to their constant arguments, so the 13-launch chain
+ * is captured once into a CUDA graph and replayed; kernels are chained with programmatic dependent launch.  Same
+ * kernels and arithmetic as the per-kernel entry points above: bit-identical results.
+ *
+ * pgf_step_state_set: (re)initialise the device state.  noise_offset / t_dp / t_model: Philox offset of the next
+ *           forward and Adam steps already taken by the DP / weight optimisers; cursor: first row of the next batch.
+ * pgf_sweep_desc: every pointer is a DEVICE pointer owned by the caller and must stay valid for the plan's life.
+ *           params / adam_m / adam_v / grads: per-model flat fp32 buffers `P` elements apart, segments at off_*;
+ *           coef: [3][n_models][D] = (w, eps_hat, d eps_hat/d DP), current on entry (pgf_dp_coeffs) and kept current;
+ *           stats_*: [n_models][4] as pgf_cls_ce writes them, of pass 1 / pass 2; logits / pred (optional): pass 2.
+ *           n_rows > 0: the cursor wraps to 0 when the next batch would run past row n_rows.
+ * pgf_sweep_plan_reset: zero the plan's internal counters (once, before the first run, on the run stream).
+ * pgf_sweep_plan_capture: record `steps_per_graph` consecutive steps into one CUDA graph on `stream`.
+ * pgf_sweep_plan_run: enqueue n_steps steps (graph replays while n_steps allows, direct launches for the rest).     */
+typedef struct pgf_sweep_desc {
+  int n_models, B, d0, d1, d2, H;
+  int dp_pass;        /* 1: two-pass step (past_acc.py); 0: pass 2 only (train.py:100-105 has pass 1 commented out) */
+  int fixed_formula;  /* eps_hat = 1/log(..) (past_acc.py:132) or log(..) (model.py:57) */
+  int use_pdl;        /* chain the kernels with programmatic dependent launch */
+  int reserved_;
+  float tau, lr, beta1, beta2, adam_eps, reserved_f_;
+  const float* x0; long long ld0;
+  const float* x1; long long ld1;
+  const float* x2; long long ld2;
+  const long long* labels;      /* [rows of the resident dataset] */
+  const long long* src_rows;    /* permutation of an epoch, indexed by the cursor; NULL = identity */
+  long long n_rows;
+  float* params; float* adam_m; float* adam_v; float* grads; long long P;
+  long long off_W1, off_b1, off_W2, off_b2, off_Wc, off_bc;
+  float* DP; float* DP_m; float* DP_v; float* dDP;
+  float* coef;
+  const float* exp_eps;
+  const unsigned long long* seeds;
+  unsigned long long row0;
+  float* stats_dp; float* stats_model;
+  float* logits; long long* pred;
+  void* state;
+  void* workspace; size_t workspace_bytes;
+} pgf_sweep_desc;
+
+int pgf_step_state_set(void* state, long long noise_offset, long long t_dp, long long t_model, long long cursor, float lr,
+                       float beta1, float beta2, void* stream);
+size_t pgf_sweep_plan_workspace(int n_models, int B, int D, int H);
+int pgf_sweep_plan_create(const pgf_sweep_desc* desc, void** plan_out);
+int pgf_sweep_plan_reset(void* plan, void* stream);
+int pgf_sweep_plan_capture(void* plan, void* stream, int steps_per_graph);
+int pgf_sweep_plan_run(void* plan, void* stream, int n_steps);
+int pgf_sweep_plan_launches_per_step(void* plan);
+int pgf_sweep_plan_destroy(void* plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -304,6 +304,50 @@ def test_adam_matches_torch(dev):
     assert torch.equal(shadow, pd.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("n_models,B,N,K", [(2, 8, 96, 256), (3, 5, 64, 192), (1, 8, 768, 2304)])
+def test_linear_adam_streaming_kernel_is_bit_identical_to_dw_plus_adam(dev, n_models, B, N, K):
+    """The TMA-fed gradient+Adam kernel (straight-line IEEE division / square-root sequences, library fallback per warp)
+    against linear_bwd_dw + adam_step (library __fdiv_rn / __fsqrt_rn), bit for bit, with moments and gradients spread
+    over the whole fp32 range: exact zeros (idle parameters), denormals, tiny and huge values."""
+    from eeg_multimodal_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(N * K + B)
+
+    def wide(shape, lo=-44.0, hi=12.0, p_zero=0.15):
+        e = torch.rand(shape, device=dev, generator=g) * (hi - lo) + lo
+        x = torch.pow(torch.tensor(10.0, device=dev), e) * torch.where(torch.rand(shape, device=dev, generator=g) < 0.5, -1.0, 1.0)
+        return torch.where(torch.rand(shape, device=dev, generator=g) < p_zero, torch.zeros_like(x), x)
+
+    P = N * K + N
+    flat = torch.randn(n_models, P, device=dev, generator=g)
+    m = wide((n_models, P), -42.0, 6.0)
+    v = wide((n_models, P), -44.0, 10.0).abs()
+    zero = torch.rand(n_models, P, device=dev, generator=g) < 0.2          # never-touched parameters: m = v = 0
+    m[zero] = 0.0
+    v[zero] = 0.0
+    dY = wide((n_models, B, N), -30.0, 3.0, p_zero=0.3)
+    X = torch.relu(torch.randn(n_models, B, K, device=dev, generator=g))   # layer inputs behind a ReLU: exact zeros
+    X[:, :, ::7] = 0.0                                                     # units that are off for the whole batch
+
+    def views(t):
+        return t[:, :N * K].view(n_models, N, K), t[:, N * K:]
+
+    for step in (1, 7):
+        a = [t.clone() for t in (flat, m, v)]
+        b = [t.clone() for t in (flat, m, v)]
+        (Wa, ba), (mWa, mba), (vWa, vba) = (views(t) for t in a)
+        ops.linear_adam_step(dY, X, Wa, mWa, vWa, ba, mba, vba, step=step, lr=1e-3)
+        grad = torch.empty_like(flat)
+        gW, gb = views(grad)
+        ops.linear_bwd_dw(dY, X, dW=gW, db=gb)
+        ops.adam_step(b[0], grad, b[1], b[2], step, lr=1e-3)
+        torch.cuda.synchronize()
+        for name, ta, tb in zip(("p", "m", "v"), a, b):
+            same = (ta == tb) | (ta.isnan() & tb.isnan())
+            assert bool(same.all()), f"step {step}: {name} differs in {int((~same).sum())} of {ta.numel()} elements"
+        flat, m, v = a
+
+
 def test_colsum_and_cast(dev):
     from eeg_multimodal_b200 import ops
 
