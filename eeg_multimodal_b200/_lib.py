@@ -25,6 +25,7 @@ SIGNATURES = {
     "pgf_num_sms": (I, []),
     "pgf_dp_coeffs": (I, [P, P, I, I, I, P, P, P, P]),
     "pgf_perturb_gate_fwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, I, LL, LL, LL, LL, LL, U64, P, P]),
+    "pgf_perturb_gate_fwd_ex": (I, [P, I, LL, P, I, LL, P, I, LL, P, P, I, I, P, P, U64, U32, U64, F, I, I, P, I, LL, P, P, P, I, LL, LL, LL, LL, LL, U64, P, P, P, I, I, P]),
     "pgf_perturb_gate_bwd_dp_workspace": (SZ, [I, I, I]),
     "pgf_perturb_gate_bwd_dp": (I, [P, I, LL, LL, I, I, I, I, P, U64, U64, P, U32, U64, P, LL, P, SZ, P, LL, I, P]),
     "pgf_minmax_norm_bwd": (I, [P, I, LL, P, I, LL, P, I, LL, P, I, LL, I, P, LL, P, LL, P, LL, P]),
@@ -95,7 +96,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful call (for the bench's `gpu_launches` count)
-LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_linear_bwd_dx": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
+LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
 launch_count = 0
 launch_by_name = {}
 

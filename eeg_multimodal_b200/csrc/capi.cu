@@ -97,13 +97,14 @@ int pgf_dp_coeffs(const float* DP, const float* exp_eps, int fixed_formula, int 
   return dp_coeffs(DP, exp_eps, fixed_formula, D, n_models, w, eps_hat, deps_dDP, static_cast<cudaStream_t>(stream));
 }
 
-int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
+int pgf_perturb_gate_fwd_ex(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
                          int d2, long long ld2, const float* w, const float* eps_hat, int B, int noise_mode,
                          const float* lap, const float* gum, unsigned long long seed, unsigned int offset,
                          unsigned long long row0, float tau, int hard, int want_gate, void* out, int out_dtype,
                          long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, int n_models,
                          long long sx0, long long sx1, long long sx2, long long s_coef, long long s_out,
-                         unsigned long long seed_step, const unsigned long long* model_seeds, void* stream) {
+                         unsigned long long seed_step, const unsigned long long* model_seeds, const void* step_state,
+                         const long long* src_rows, int gather, int n_rep, void* stream) {
   if (B == 0 || n_models == 0) return PGF_OK;  // empty batch: nothing to do
   PGF_CHECK_ARG(n_models > 0 && (sx0 % 4) == 0 && (sx1 % 4) == 0 && (sx2 % 4) == 0 && (s_coef % 4) == 0 && (s_out % 4) == 0,
                 "pgf_perturb_gate_fwd: n_models < 0 or model strides not multiples of 4");
@@ -122,6 +123,7 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   bool gate = want_gate != 0 && noise_mode != PGF_NOISE_NONE;
   if (noise_mode == PGF_NOISE_INJECTED && !gum) gate = false;
   PGF_CHECK_ARG(tau > 0.f, "pgf_perturb_gate_fwd: tau must be > 0");
+  PGF_CHECK_ARG(n_rep >= 1 && n_rep <= 4096, "pgf_perturb_gate_fwd_ex: n_rep must be in 1..4096");
   PerturbFwdArgs a = {};
   a.n_rep = 1;
   a.x[0] = x0; a.x[1] = x1; a.x[2] = x2;
@@ -136,7 +138,20 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
   a.seed = seed; a.offset = offset; a.row0 = row0;
   a.tau = tau; a.inv_tau = 1.0f / tau; a.hard = hard;
   a.out = out; a.ld_out = ld_out; a.gate_idx = gate_idx; a.row_min = row_min; a.row_max = row_max;
+  a.st = static_cast<const StepState*>(step_state); a.src_rows = src_rows; a.gather = gather != 0; a.n_rep = n_rep;
   return perturb_gate_fwd(a, noise_mode, out_dtype, gate, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1, const float* x2,
+                         int d2, long long ld2, const float* w, const float* eps_hat, int B, int noise_mode,
+                         const float* lap, const float* gum, unsigned long long seed, unsigned int offset,
+                         unsigned long long row0, float tau, int hard, int want_gate, void* out, int out_dtype,
+                         long long ld_out, unsigned char* gate_idx, float* row_min, float* row_max, int n_models,
+                         long long sx0, long long sx1, long long sx2, long long s_coef, long long s_out,
+                         unsigned long long seed_step, const unsigned long long* model_seeds, void* stream) {
+  return pgf_perturb_gate_fwd_ex(x0, d0, ld0, x1, d1, ld1, x2, d2, ld2, w, eps_hat, B, noise_mode, lap, gum, seed, offset, row0, tau,
+                                 hard, want_gate, out, out_dtype, ld_out, gate_idx, row_min, row_max, n_models, sx0, sx1, sx2, s_coef,
+                                 s_out, seed_step, model_seeds, nullptr, nullptr, 0, 1, stream);
 }
 
 size_t pgf_perturb_gate_bwd_dp_workspace(int B, int D, int n_models) {

@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(CE_THREADS, 2) cls_ce_kernel(const CeArgs a) {
     const int label = labels ? static_cast<int>(labels[lrow]) : 0;
     const float m = fmaxf(z0, z1);
     const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
-    const float loss = lse - (label == 0 ? z0 : z1);
+    // a label outside {0,1} (F.cross_entropy raises on it) poisons the loss statistic with NaN instead of being scored silently
+    const float loss = (label == 0 || label == 1) ? lse - (label == 0 ? z0 : z1) : __int_as_float(0x7fc00000);
     const int pred = z1 > z0 ? 1 : 0;  // torch.argmax: first index on ties
     if (lane == 0) {
       if (a.logits) *reinterpret_cast<float2*>(a.logits + model * a.slogits + row * 2) = make_float2(z0, z1);

@@ -174,14 +174,22 @@ class HeadEngine:
             self._coef_key = key
         return coef
 
-    def _perturb(self, blocks, hard, out, row0):
-        """kernel (a) for every model; returns the per-model coefficient rows and the noise spec."""
+    def _perturb(self, blocks, hard, out, row0, n_rep=1):
+        """kernel (a) for every model; returns the per-model coefficient rows and the noise spec.  n_rep > 1 (evaluation
+        only): the batch is perturbed n_rep times with consecutive Philox offsets in one launch (train.py:126-131)."""
         M, D = self.M, self.D
         coef = self._ensure_coef()
         inj = self._injected
         self._injected = None
         offset = self.noise_offset
-        self.noise_offset += 1
+        self.noise_offset += n_rep
+        if n_rep > 1:
+            if inj is not None:
+                raise ValueError("repeated evaluation draws its noise in-kernel (no injected tensors)")
+            kw = dict(seed=self.seeds[0], seed_step=self.seed_step) if self.seed_step is not None else dict(model_seeds=self.seeds_dev)
+            ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_PHILOX, offset=offset, row0=row0, tau=self.tau, hard=hard,
+                                 out=out, n_models=M, n_rep=n_rep, **kw)
+            return coef, (None, offset)
         if inj is not None:
             ops.perturb_gate_fwd(blocks, coef[0], coef[1], noise_mode=L.NOISE_INJECTED, lap=inj[0], gum=inj[1], tau=self.tau,
                                  hard=hard, want_gate=inj[1] is not None, out=out, n_models=M)
@@ -228,24 +236,38 @@ class HeadEngine:
         return dict(logits=self._buf("logits_" + mode, (M, B, 2), torch.float32), pred=self._buf("pred_" + mode, (M, B), torch.int64),
                     stats=self._buf("stats_" + mode, (M, 4), torch.float32))
 
-    def _labels(self, labels):
-        labels = labels.reshape(labels.shape[0], -1)[:, 0] if labels.dim() == 2 and labels.shape[-1] == 1 else labels
+    def _labels(self, labels, B=None):
+        """int64 labels as the kernels take them: [B] shared by every model, or [M,B] per model.  Accepted inputs: [B], the
+        reference's [B,1] column (past_acc.py:71 squeezes it), or [M,B]; with `B` (the batch size of the feature blocks) given
+        the shape is checked against it, so that a [M,1] per-model tensor of a 1-row tail batch is not mistaken for a column."""
+        if labels.dim() == 2:
+            if B is not None and labels.shape == (self.M, B) and not (labels.shape[1] == 1 and labels.shape[0] == B):
+                pass                                        # per-model labels
+            elif labels.shape[1] == 1 and (B is None or labels.shape[0] == B):
+                labels = labels[:, 0]                       # the reference's [B,1] column
+            elif B is not None:
+                raise ValueError(f"labels of shape {tuple(labels.shape)} match neither [B]=[{B}], [B,1] nor [M,B]=[{self.M},{B}]")
+        elif labels.dim() != 1 or (B is not None and labels.shape[0] != B):
+            raise ValueError(f"labels of shape {tuple(labels.shape)} do not match the batch of {B} rows")
         return labels.contiguous()
 
     # ---- one forward(+backward) pass -----------------------------------------------------------
-    def _pass(self, blocks, labels, hard, mode, row0=0, global_batch=None, fuse_adam=False):
+    def _pass(self, blocks, labels, hard, mode, row0=0, global_batch=None, fuse_adam=False, n_rep=1):
         """mode: 'dp' (pass 1), 'model' (pass 2) or 'eval'.  Returns the cls_ce result dict.
         fuse_adam (fp32 path, batch <= 8, no gradient all-reduce): the Adam step of pass 2 is applied inside the
         pass, with the weight gradients recomputed in the optimiser kernel instead of written to HBM;
         res['adam_done'] tells the caller."""
-        B = blocks[0].shape[-2]
+        B = blocks[0].shape[-2] * n_rep        # n_rep > 1 (eval): the repetitions are further batch rows, repetition-major
         M, D, H = self.M, self.D, self.H
         gb = float(global_batch or B)
+        if n_rep > 1:
+            assert mode == "eval"
+            labels = labels.repeat(n_rep) if labels.dim() == 1 else labels.repeat(1, n_rep)
         W1, b1, W2, b2, Wc, bc = (self.view(n) for n in ("W1", "b1", "W2", "b2", "Wc", "bc"))
         backward = mode != "eval"
         if self.precision == "fp32":
             X = self._buf("X", (M, B, D), torch.float32)
-            coef, nspec = self._perturb(blocks, hard, X, row0)
+            coef, nspec = self._perturb(blocks, hard, X, row0, n_rep)
             H1 = ops.linear_fwd(X, W1, b1, L.ACT_RELU, out=self._buf("H1", (M, B, D), torch.float32))
             H2 = ops.linear_fwd(H1, W2, b2, L.ACT_TANH, out=self._buf("H2", (M, B, H), torch.float32))
             res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward, **self._ce_out(mode, B),
@@ -276,7 +298,7 @@ class HeadEngine:
         if mode == "model":   # the split-K weight-gradient GEMMs accumulate into a zeroed buffer
             ops.fill_zero(self.grad)
         X = self._buf("Xh", (M, B, D), bf)
-        coef, nspec = self._perturb(blocks, hard, X, row0)
+        coef, nspec = self._perturb(blocks, hard, X, row0, n_rep)
         H1 = self._buf("H1h", (M, B, D), bf)
         H2 = self._buf("H2f", (M, B, H), torch.float32)  # tanh output kept in fp32: exact logits / loss
         W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
@@ -337,13 +359,14 @@ class HeadEngine:
     def _train_step_planned(self, blocks, labels, row0, global_batch, grad_hook, dp_pass):
         """Launch-bound regimes: record the C-ABI calls of two steps with this input signature, then replay them
         (ops.CallPlan) -- same functions, buffers and order, none of the Python between the launches."""
-        labels = self._labels(labels)
+        labels = self._labels(labels, blocks[0].shape[-2])
         blocks = [b.contiguous() for b in blocks]
         key = (tuple((tuple(b.shape), tuple(b.stride()), b.dtype) for b in blocks), tuple(labels.shape), tuple(labels.stride()),
                global_batch, bool(dp_pass), grad_hook is not None, ops._stream())   # a plan replays on the stream it was recorded on
         ent = self._plans.get(key)
         inputs = {("block", i): b.data_ptr() for i, b in enumerate(blocks)}
         inputs["labels"] = labels.data_ptr()
+        extents = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in (*blocks, labels)]
         if ent is not None and "plan" in ent:
             n, rem = divmod(self.t_model - ent["state"][2], 1)
             d = ent["dstate"]
@@ -371,22 +394,22 @@ class HeadEngine:
             ops.RECORD = None
         ptrs = {v: k for k, v in inputs.items()}
         if ent is None:
-            self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs)
+            self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs, extents=extents)
         else:
             apart = state[2] - ent["state"][2]
             try:
                 if apart < 1:
                     raise RuntimeError("recorded steps out of order")
-                plan = ops.CallPlan(ent["rec"], rec, ent["ptrs"], ptrs, steps_apart=apart)
+                plan = ops.CallPlan(ent["rec"], rec, ent["ptrs"], ptrs, steps_apart=apart, input_extents=ent["extents"] + extents)
                 dstate = tuple((b - a) // apart for a, b in zip(ent["state"], state))
                 self._plans[key] = dict(plan=plan, state=ent["state"], dstate=dstate, row0=ent["row0"],
                                         drow0=(row0 - ent["row0"]) // apart, stats=self._buf("stats_model", (self.M, 4), torch.float32))
             except RuntimeError:
-                self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs)   # start over from this step
+                self._plans[key] = dict(rec=rec, state=state, row0=row0, ptrs=ptrs, extents=extents)   # start over from this step
         return result
 
     def _train_step(self, blocks, labels, row0, global_batch, grad_hook, dp_pass):
-        labels = self._labels(labels)
+        labels = self._labels(labels, blocks[0].shape[-2])
         blocks = [b.contiguous() for b in blocks]
         if dp_pass:   # dp_pass=False reproduces train.py, where the DP pass is commented out (train.py:100-105)
             self._pass(blocks, labels, hard=False, mode="dp", row0=row0, global_batch=global_batch)
@@ -415,10 +438,17 @@ class HeadEngine:
         return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], stats=st)   # stats [M,4] = {loss, n_correct, acc, B}
 
     @torch.no_grad()
-    def eval_step(self, blocks, labels, row0=0):
-        """past_acc.py:218-228: hard=True, noise still sampled.  Returns dict(loss, acc, pred, logits)."""
-        labels = self._labels(labels)
+    def eval_step(self, blocks, labels, row0=0, n_eval=1):
+        """past_acc.py:218-228: hard=True, noise still sampled.  Returns dict(loss, acc, pred, logits).
+        n_eval > 1: the n_eval repeated stochastic evaluations of train.py:126-131 as ONE batched pass (n_eval Philox
+        offsets inside one launch of every kernel); pred / logits are then [M, n_eval, B(, 2)], loss / acc the means over
+        all repetitions."""
+        labels = self._labels(labels, blocks[0].shape[-2])
+        B = blocks[0].shape[-2]
         with ops.stream_scope():
-            res = self._pass([b.contiguous() for b in blocks], labels, hard=True, mode="eval", row0=row0)
+            res = self._pass([b.contiguous() for b in blocks], labels, hard=True, mode="eval", row0=row0, n_rep=int(n_eval))
         st = res["stats"].view(self.M, 4)
-        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], pred=res["pred"], logits=res["logits"])
+        pred, logits = res["pred"], res["logits"]
+        if n_eval > 1:
+            pred, logits = pred.view(self.M, n_eval, B), logits.view(self.M, n_eval, B, 2)
+        return dict(loss=st[:, 0], acc=st[:, 2], n_correct=st[:, 1], pred=pred, logits=logits)

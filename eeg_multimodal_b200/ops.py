@@ -116,9 +116,15 @@ class CallPlan:
     Replaying is then one ctypes call per kernel with the same C functions, same buffers, same order: results are
     bit-identical to the wrapper path (tests/test_gpu_model.py)."""
 
-    def __init__(self, rec_a, rec_b, input_ptrs, input_ptrs_b=None, steps_apart=1):
-        """input_ptrs / input_ptrs_b: {data pointer: key} of the caller's input tensors in the two recorded steps."""
+    def __init__(self, rec_a, rec_b, input_ptrs, input_ptrs_b=None, steps_apart=1, input_extents=()):
+        """input_ptrs / input_ptrs_b: {data pointer: key} of the caller's input tensors in the two recorded steps;
+        input_extents: [lo, hi) address ranges of those tensors' storage -- a pointer argument that lies INSIDE one of them
+        without being its base (a slice such as blocks[i] of a [M,B,D] input) cannot be substituted on replay and would keep
+        reading the recorded step's memory, so such a sequence is refused (the caller then stays on the wrapper path)."""
         input_ptrs_b = input_ptrs if input_ptrs_b is None else input_ptrs_b
+
+        def derived(ptr):
+            return ptr is not None and any(lo < ptr < hi for lo, hi in input_extents)
         if len(rec_a) != len(rec_b) or any(a[1] != b[1] or len(a[2]) != len(b[2]) for a, b in zip(rec_a, rec_b)):
             raise RuntimeError("the two recorded steps issued different call sequences")
         lib = L.load()
@@ -137,6 +143,9 @@ class CallPlan:
                         sub.append((i, input_ptrs[x]))
                     elif x != y:
                         raise RuntimeError(f"{name}: pointer argument {i} changed between the recorded steps (buffers must be stable)")
+                    elif derived(x):
+                        raise RuntimeError(f"{name}: pointer argument {i} points into a caller input tensor (a slice of it): "
+                                           "a replay with other inputs would read stale memory")
                 elif x != y:
                     if not (isinstance(x, int) and isinstance(y, int)) or (y - x) % steps_apart:
                         raise RuntimeError(f"{name}: argument {i} changed between steps in a way a plan cannot replay ({x} -> {y})")
@@ -216,24 +225,34 @@ def dp_coeffs(DP: torch.Tensor, exp_eps, fixed: bool = True, out=None):
 
 def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed=0, offset=0, row0=0, tau=1.0,
                      hard=True, want_gate=False, out_dtype=torch.float32, out=None, want_gate_idx=False,
-                     want_minmax=False, n_models=1, seed_step=0, model_seeds=None):
+                     want_minmax=False, n_models=1, seed_step=0, model_seeds=None, n_rep=1, src_rows=None, cursor_state=None):
     """models.py:69-79 in one kernel.  Returns (out, gate_idx|None, row_min|None, row_max|None).
     Single model: blocks [B,Di], out [B,D].  Grouped (n_models > 1): blocks [B,Di] (shared batch) or
-    [M,B,Di]; w/eps_hat [M,D]; out [M,B,D]; lap [M,B,D]; gum [M,2,B,D]; model m uses seed + m*seed_step."""
+    [M,B,Di]; w/eps_hat [M,D]; out [M,B,D]; lap [M,B,D]; gum [M,2,B,D]; model m uses seed + m*seed_step.
+    n_rep > 1: the batch is perturbed n_rep times with offsets offset..offset+n_rep-1 in one launch (the n_eval
+    repetitions of train.py:126-131); out then has n_rep*B rows, repetition-major.  src_rows (device int64): the
+    batch is rows src_rows[0:B] of the (resident) blocks."""
     blocks = [_chk(b, torch.float32, "feature block") for b in blocks]
     if not 1 <= len(blocks) <= 3:
         raise ValueError("1 to 3 feature blocks expected")
-    B = blocks[0].shape[-2]
+    n_rep = int(n_rep)
+    gather = src_rows is not None
+    B = int(src_rows.numel()) if gather else blocks[0].shape[-2]
+    if gather:
+        _chk(src_rows, torch.int64, "src_rows")
+        assert src_rows.is_contiguous()
     dims = [b.shape[-1] for b in blocks]
     D = sum(dims)
     dev = blocks[0].device
     M = int(n_models)
     lead = (M,) if M > 1 or (out is not None and out.dim() == 3) else ()
     if out is None:
-        out = torch.empty(*lead, B, D, dtype=out_dtype, device=dev)
-    gate_idx = torch.empty(*lead, B, D, dtype=torch.uint8, device=dev) if (want_gate and want_gate_idx) else None
-    rmin = torch.empty(*lead, B, dtype=torch.float32, device=dev) if want_minmax else None
-    rmax = torch.empty(*lead, B, dtype=torch.float32, device=dev) if want_minmax else None
+        out = torch.empty(*lead, n_rep * B, D, dtype=out_dtype, device=dev)
+    elif out.shape[-2] != n_rep * B:
+        raise ValueError(f"out must have n_rep*B = {n_rep * B} rows, got {out.shape[-2]}")
+    gate_idx = torch.empty(*lead, n_rep * B, D, dtype=torch.uint8, device=dev) if (want_gate and want_gate_idx) else None
+    rmin = torch.empty(*lead, n_rep * B, dtype=torch.float32, device=dev) if want_minmax else None
+    rmax = torch.empty(*lead, n_rep * B, dtype=torch.float32, device=dev) if want_minmax else None
     bl = blocks + [None] * (3 - len(blocks))
     args, sx = [], []
     for b in bl:
@@ -241,16 +260,21 @@ def perturb_gate_fwd(blocks, w, eps_hat, *, noise_mode, lap=None, gum=None, seed
         sx.append(0 if b is None or b.dim() == 2 else b.stride(0))
     if lap is not None:
         _chk(lap, torch.float32, "lap")
-        assert lap.is_contiguous() and lap.numel() == M * B * D
+        assert lap.is_contiguous() and lap.numel() == M * n_rep * B * D
     if gum is not None:
         _chk(gum, torch.float32, "gum")
-        assert gum.is_contiguous() and gum.numel() == M * 2 * B * D
+        assert gum.is_contiguous() and gum.numel() == M * 2 * n_rep * B * D
     s_coef = 0 if w is None or w.dim() == 1 else w.stride(0)
     s_out = out.stride(0) if out.dim() == 3 else 0
-    _call(("perturb_fwd", B, D, M, _dt(out), noise_mode, int(bool(want_gate)), int(M > 1 and not any(sx))), "pgf_perturb_gate_fwd", *args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
-           int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
-           out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
-           _seeds_ptr(model_seeds, M), _stream())
+    common = (*args, _ptr(w), _ptr(eps_hat), B, noise_mode, _ptr(lap), _ptr(gum), int(seed),
+              int(offset) & 0xFFFFFFFF, int(row0), float(tau), int(bool(hard)), int(bool(want_gate)), out.data_ptr(), _dt(out),
+              out.stride(-2), _ptr(gate_idx), _ptr(rmin), _ptr(rmax), M, sx[0], sx[1], sx[2], s_coef, s_out, int(seed_step),
+              _seeds_ptr(model_seeds, M))
+    tag = ("perturb_fwd", n_rep * B, D, M, _dt(out), noise_mode, int(bool(want_gate)), int(M > 1 and not any(sx)))
+    if n_rep > 1 or gather or cursor_state is not None:
+        _call(tag, "pgf_perturb_gate_fwd_ex", *common, _ptr(cursor_state), _ptr(src_rows), int(gather), n_rep, _stream())
+    else:
+        _call(tag, "pgf_perturb_gate_fwd", *common, _stream())
     return out, gate_idx, rmin, rmax
 
 

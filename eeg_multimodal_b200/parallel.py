@@ -80,6 +80,19 @@ def gather_metrics(local: dict, group=None):
     return dict(sorted(merged.items()))
 
 
+def gather_results(local: dict, group=None):
+    """Host-side gather of per-model result dicts {model_index: {...}} from all ranks.  Every rank must call it -- also
+    one that owns no model (world size larger than the grid) and passes {} -- or the collective hangs."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(sorted(local.items()))
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    merged = {}
+    for d in out:
+        merged.update(d)
+    return dict(sorted(merged.items()))
+
+
 class StreamedEnsemble:
     """One GPU's share of a sweep as G independent model groups (HeadEngines), each on its own CUDA stream.
 

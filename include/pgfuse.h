@@ -87,6 +87,23 @@ int pgf_perturb_gate_fwd(const float* x0, int d0, long long ld0, const float* x1
                          long long s_coef, long long s_out, unsigned long long seed_step,
                          const unsigned long long* model_seeds, void* stream);
 
+/* The same kernel with the three extensions the training / evaluation drivers use (all optional, NULL / 0 / 1 = off):
+ *   step_state (pgf_step_state, device): offset += state.noise_offset;
+ *   gather != 0: batch row b is row src_rows[cursor + b] (src_rows NULL: cursor + b) of the RESIDENT blocks x0..x2,
+ *                cursor = state.cursor (0 without a state) -- a shuffled epoch without host work (data.py:37-45);
+ *   n_rep > 1:   the batch is perturbed n_rep times with Philox offsets offset .. offset+n_rep-1, i.e. the n_eval
+ *                repeated stochastic evaluations of train.py:126-131 in ONE launch; out (and row_min/row_max,
+ *                gate_idx, lap, gum) then have n_rep*B rows per model, repetition-major.                            */
+int pgf_perturb_gate_fwd_ex(const float* x0, int d0, long long ld0, const float* x1, int d1, long long ld1,
+                            const float* x2, int d2, long long ld2, const float* w, const float* eps_hat, int B,
+                            int noise_mode, const float* lap, const float* gum, unsigned long long seed,
+                            unsigned int offset, unsigned long long row0, float tau, int hard, int want_gate,
+                            void* out, int out_dtype, long long ld_out, unsigned char* gate_idx, float* row_min,
+                            float* row_max, int n_models, long long sx0, long long sx1, long long sx2,
+                            long long s_coef, long long s_out, unsigned long long seed_step,
+                            const unsigned long long* model_seeds, const void* step_state, const long long* src_rows,
+                            int gather, int n_rep, void* stream);
+
 /* ---- (a11) dL/dDP through the perturbation ----------------------------------------------------
  * replaces: autograd through models.py:75-76: dDP[d] = deps_dDP[d] * sum_b dF[b,d] * noise[b,d]
  *           (the gate's own contribution is zero in exact arithmetic).

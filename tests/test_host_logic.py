@@ -177,6 +177,92 @@ def test_call_plan_logic_with_a_stub_library(monkeypatch):
         ops.CallPlan([fill], [fill, fill], {})
 
 
+def test_call_plan_refuses_pointers_into_caller_inputs(monkeypatch):
+    """A pointer argument that lies inside a caller input tensor without being its base (blocks[i] of a [M,B,D] input)
+    compares equal between two recorded steps that used the same tensors, but cannot be substituted on replay: refused."""
+    from eeg_multimodal_b200 import _lib, ops
+
+    class Stub:
+        def __getattr__(self, name):
+            return lambda *a: 0
+
+    monkeypatch.setattr(_lib, "_lib", Stub())
+    fill = lambda p: (("fill",), "pgf_fill_zero", (p, 64, 77))
+    # base pointer 1000 (substituted), slice pointer 1000 + 256 inside the same storage [1000, 2024)
+    ok = ops.CallPlan([fill(1000)], [fill(1000)], {1000: "x"}, {1000: "x"}, input_extents=[(1000, 2024)])
+    assert ok.calls[0][5] == [(0, "x")]
+    with pytest.raises(RuntimeError, match="points into a caller input"):
+        ops.CallPlan([fill(1000), fill(1256)], [fill(1000), fill(1256)], {1000: "x"}, {1000: "x"}, input_extents=[(1000, 2024)])
+
+
+def test_driver_refuses_flags_it_would_reinterpret():
+    from eeg_multimodal_b200 import train
+
+    p = train.build_parser()
+    train._reject_unsupported(p.parse_args([]))
+    train._reject_unsupported(p.parse_args(["--n_dp", "0"]))
+    for bad in (["--n_para", "2"], ["--n_dp", "3"], ["--n_class", "3"]):
+        with pytest.raises(NotImplementedError):
+            train._reject_unsupported(p.parse_args(bad))
+
+
+def test_reference_results_layout():
+    """results.pth keys / shapes of train.py:131-144 for one model: everything a torch.cat over epochs."""
+    from eeg_multimodal_b200 import train
+
+    N, ne, D = 13, 5, 24
+    ep = lambda: dict(train_loss=torch.rand(40), logits=torch.rand(N, ne, 2), pred=torch.zeros(N, ne, dtype=torch.int64),
+                      val_loss=torch.rand(N, ne), Accuracy=torch.rand(ne), F1Score=torch.rand(ne), DP_params=torch.zeros(1, D))
+    r = train.reference_results([ep(), {"train_loss": torch.rand(40)}, ep()], ne)
+    assert r["logits"].shape == (2 * N, ne, 2) and r["pred"].shape == (2 * N, ne) and r["val_loss"].shape == (2 * N, ne)
+    assert r["train_loss"].shape == (120,) and r["Accuracy"].shape == (2 * ne,) and r["DP_params"].shape == (2, D)
+
+
+def test_resident_dataset_follows_the_host_loader_order():
+    """ResidentDataset (device-side gather through one permutation per epoch) yields the batches FeatureLoader / a
+    DataLoader(shuffle=True) with the same generator would, incl. the partial last batch (data.py:41-42)."""
+    blocks, labels = fc.synthetic_features(21, dims=(8, 4), seed=3)
+    a = fc.ResidentDataset(blocks, labels, 8, shuffle=True, seed=5, device="cpu")
+    b = fc.FeatureLoader(blocks, labels, 8, shuffle=True, seed=5, device="cpu")
+    for _ in range(2):                                           # two epochs: the generator state carries over
+        sizes = []
+        for (gb, gl), (wb, wl) in zip(a, b):                      # in lockstep: the host loader reuses its staging buffers
+            assert torch.equal(gl, wl) and all(torch.equal(x, y) for x, y in zip(gb, wb))
+            sizes.append(gl.shape[0])
+        assert sizes == [8, 8, 5]
+    assert a.n_full == 2
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "feature/test_EEG.csv")), reason="reference checkout not present")
+def test_reference_split_converter_reads_the_shipped_files(tmp_path):
+    """The reference's own dataset files (data.py:7-35) -> the tensors its Dataset yields -> feature cache, through a
+    stand-in encoder (the real BERT / CLIP-projection / cross-attention stack is out of scope)."""
+    args = [os.path.join(REF, p) for p in ("feature/test_EEG.csv", "feature/action/test_clip_v2.pickle", "feature/EEG/test_bert.pickle")]
+    raw = fc.read_reference_split(*args)
+    assert raw["frame_input"].shape == (601, 1, 512) and raw["frame_input"].dtype == torch.float32
+    assert raw["title_input"].shape == (601, 512) and raw["text_mask"].shape == (601, 512) and raw["vedio_mask"].shape == (601, 1)
+    assert raw["title_input"][0, 0] == 101 and int(raw["label"].sum()) == 411               # [CLS]; 411 positives of 601
+    assert torch.equal(raw["text_mask"], (raw["title_input"] != 0).long())
+
+    def encoder(x):                                              # 4-tuple of data.py -> three [B,768] blocks
+        frame, vmask, ids, tmask = x
+        g = torch.Generator().manual_seed(0)
+        proj = torch.randn(512, 768, generator=g) / 512 ** 0.5
+        emb = torch.randn(30522, 768, generator=g)
+        pooled = (emb[ids] * tmask[..., None]).sum(1) / tmask.sum(1, keepdim=True)
+        vis = frame[:, 0] @ proj
+        return pooled, vis, pooled * vis
+
+    out = str(tmp_path / "test_split.npz")
+    blocks, labels = fc.convert_reference_split(*args, encoder, out, batch_size=128)
+    back, lab = fc.load_features(out)
+    assert [tuple(b.shape) for b in back] == [(601, 768)] * 3 and torch.equal(lab, raw["label"])
+    assert all(torch.equal(a, b) for a, b in zip(back, blocks))
+
+
 def test_launch_accounting_follows_the_single_launch_paths():
     """bench.py's `gpu_launches` is a claim: pgf_cls_ce (B <= 8) and pgf_perturb_gate_bwd_dp (B <= 32) finish in their
     main kernel, everything else as tabulated."""

@@ -70,6 +70,31 @@ def test_world2_gloo_allreduce_and_gather(tmp_path):
     assert res[0]["merged"] == res[1]["merged"]
 
 
+def _worker_small_grid(rank, world, port, out_dir):
+    """A 1-model grid on 2 ranks: rank 1 owns nothing and must still take part in every collective of the driver's tail
+    (eeg_multimodal_b200/train.py: gather_metrics + gather_results), or rank 0 hangs before results.pth is written."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    parallel.init_distributed("gloo")
+    grid = parallel.sweep_grid([1.0], 1)
+    mine = [grid[i] for i in parallel.shard_models(len(grid), world, rank)]
+    local = {g["index"]: {"best_acc": 0.75, "reference": {"Accuracy": torch.tensor([0.75])}} for g in mine}
+    merged = parallel.gather_metrics({i: r["best_acc"] for i, r in local.items()})
+    everything = parallel.gather_results(local)
+    torch.save({"n_mine": len(mine), "merged": merged, "keys": list(everything)}, os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world2_gloo_rank_without_models_joins_the_gathers(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_small_grid, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"s{r}.pt") for r in range(world)]
+    assert [r["n_mine"] for r in res] == [1, 0]
+    for r in res:
+        assert r["merged"] == {0: 0.75} and r["keys"] == [0]
+
+
 def test_single_process_paths_need_no_process_group():
     os.environ.pop("WORLD_SIZE", None)
     assert parallel.init_distributed("gloo") == (int(os.environ.get("RANK", "0")), 1)
@@ -77,3 +102,4 @@ def test_single_process_paths_need_no_process_group():
     parallel.make_allreduce_hook()(t)                               # no-op without a group
     assert torch.equal(t, torch.ones(3))
     assert parallel.gather_metrics({1: 0.5}) == {1: 0.5}
+    assert parallel.gather_results({2: {"a": 1}, 1: {"a": 0}}) == {1: {"a": 0}, 2: {"a": 1}}
