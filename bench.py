@@ -58,6 +58,8 @@ def parse():
                     help="sweep48_b8: the fused, graph-replayed step (pgf_sweep_plan_*) instead of one C-ABI call per kernel")
     ap.add_argument("--graph-steps", type=int, default=4, help="sweep48_b8 plan: steps per CUDA graph (0 = direct launches, no graph)")
     ap.add_argument("--no-pdl", action="store_true", help="sweep48_b8 plan: no programmatic dependent launch")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"],
+                    help="sweep_synth64k / dp64k: arithmetic of the dense layers (fp32x3 = fp32 parity on the tensor cores)")
     ap.add_argument("--no-also", action="store_true", help="default workload: skip the secondary measurements in config.also")
     return ap.parse_args()
 
@@ -140,6 +142,12 @@ def kernel_work(tag):
     if kind == "gemm":
         _, m, n, k, a_mn, b_mn, epi = tag
         return f"gemm_bf16_tc M={m} N={n} K={k} a_mn={a_mn} b_mn={b_mn} epi={epi}", "tensor", 2.0 * m * n * k
+    if kind == "gemm_x3":   # six bf16 plane-pair products per fp32 multiply-add: tensor work = 6 x 2MNK
+        _, m, n, k, a_mn, b_mn, epi = tag
+        return f"gemm_bf16x3_tc M={m} N={n} K={k} a_mn={a_mn} b_mn={b_mn} epi={epi}", "tensor", 12.0 * m * n * k
+    if kind == "split3":
+        _, r, c, act, planes, out, mask = tag
+        return f"split3 R={r} C={c} act={act} planes={planes} out={out} mask={mask}", "hbm", float(r) * c * (4 + 6 * planes + 4 * out + 2 * mask)
     if kind == "perturb_fwd":
         _, b, d, m, dt, noise, gate, shared = tag
         osz = 4 if dt == 0 else 2   # a batch shared by the sweep is read once, every model writes its own perturbed copy
@@ -318,6 +326,45 @@ def measure_sweep_b8_plan(dev, rank, world, M, K, W, graph_steps=4, use_pdl=True
 
 
 # --------------------------------------------------------------------------------------------------
+def measure_fp32x3(dev, world, B, dims, nres=4, K=6, W=3):
+    """The precision cost as a measured number: ONE model's reference two-pass step on the large synthetic batch with the
+    dense layers held to fp32 arithmetic on the tensor cores (HeadEngine precision='fp32x3': hi/mid/lo bf16 planes, six
+    plane-pair products, 1e-5 bar) next to the same step with bf16 GEMM operands (2e-2 bar), same process, same batches."""
+    import torch
+    import torch.distributed as dist
+
+    from eeg_multimodal_b200 import HeadEngine
+
+    g = torch.Generator(device=dev).manual_seed(7)
+    data = [([torch.rand(B, d, device=dev, generator=g) for d in dims], (torch.rand(B, device=dev, generator=g) < 0.66).long())
+            for _ in range(nres)]
+    D, H = sum(dims), HIDDEN
+    out = {"workload": f"one model, batch {B} x {list(dims)}, reference two-pass step incl. both Adam updates", "steps": K,
+           "l2": f"{nres} resident batches of {D * B * 4 / 1e6:.0f} MB cycled"}
+    for prec in ("fp32x3", "bf16"):
+        eng = HeadEngine(n_models=1, feature_dims=dims, hidden=H, eps=1.0, precision=prec)
+        for i in range(W):
+            eng.train_step(*data[i % nres])
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(K):
+            eng.train_step(*data[i % nres])
+        t1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([t0.elapsed_time(t1) / K], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[prec] = {"value": world * B / (float(ms) * 1e-3), "unit": "model-samples/s", "ms_per_step": float(ms)}
+        del eng
+        torch.cuda.empty_cache()
+    peaks, _ = measured_peaks()
+    flop = 6.0 * flops_per_sample_step(D, H) * B      # bf16 tensor flops of the fp32x3 step: six plane-pair products
+    out["fp32x3"]["tensor_frac_step"] = flop / (out["fp32x3"]["ms_per_step"] * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out["fp32_parity_cost"] = out["fp32x3"]["ms_per_step"] / out["bf16"]["ms_per_step"]
+    return out
+
+
 def cpu_reference_leg(args, steps, warmup, sample):
     """The reference's CPU path (oracle restatement incl. the reference's own host noise calls),
     all host threads, on a bounded sample of the workload.  Returns (samples/s, cores, sample str)."""
@@ -443,10 +490,10 @@ def run_ours(args):
         dims, B, M, precision = (768, 768, 768), 8, args.models_per_gpu, "fp32"
         D = 2304
     elif args.workload == "dp64k":
-        dims, M, precision = DIMS, 1, "bf16"
+        dims, M, precision = DIMS, 1, args.precision
         B = args.batch // world
     else:
-        dims, M, precision = DIMS, args.models_per_gpu, "bf16"
+        dims, M, precision = DIMS, args.models_per_gpu, args.precision
     eps = [EPS_SET[(rank * M + i) % len(EPS_SET)] for i in range(M)]
     seeds = [980616 + (rank * M + i) // len(EPS_SET) for i in range(M)] if args.workload != "dp64k" else [980616]
     # launch-bound sweep: the GPU's models as G independent groups on G streams, whose short kernels overlap
@@ -595,6 +642,8 @@ def run_ours(args):
         also = {"sweep48_b8": {k: r8[k] for k in ("workload", "models_per_gpu", "models_total", "value", "unit", "ms_per_step", "steps",
                                                    "launches_per_step", "graph_steps", "pdl", "hbm_frac_step", "hbm_frac_step_vs_8tbs",
                                                    "hbm_gbs_step", "e2e")}}
+
+        also["fp32x3_synth64k"] = measure_fp32x3(dev, world, B, dims, nres=4)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

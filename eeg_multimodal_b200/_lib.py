@@ -34,6 +34,8 @@ SIGNATURES = {
     "pgf_linear_bwd_dx": (I, [P, LL, LL, P, LL, P, I, LL, LL, P, LL, LL, I, I, I, I, P, SZ, P]),
     "pgf_linear_bwd_dw": (I, [P, LL, LL, P, LL, LL, P, LL, P, LL, I, I, I, I, I, P]),
     "pgf_gemm_bf16": (I, [P, LL, I, P, LL, I, P, LL, I, I, I, I, P, P, LL, I, P, P]),
+    "pgf_split3": (I, [P, LL, I, I, P, I, P, LL, P, LL, P, LL, LL, P]),
+    "pgf_gemm_bf16x3": (I, [P, LL, LL, I, P, LL, LL, I, P, LL, I, I, I, I, P, I, P]),
     "pgf_gemm_partial_rows": (I, [I]),
     "pgf_reduce_partials": (I, [P, I, I, P, P, I, P]),
     "pgf_gemm_bf16_ddp": (I, [P, LL, P, LL, I, I, I, I, U64, U32, U64, P, P, SZ, P, I, P]),

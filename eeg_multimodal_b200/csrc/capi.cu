@@ -267,6 +267,39 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
   return gemm_bf16(A, lda, a_mn, B, ldb, b_mn, g, static_cast<cudaStream_t>(stream));
 }
 
+int pgf_gemm_bf16x3(const void* A3, long long lda, long long a_plane, int a_mn, const void* B3, long long ldb, long long b_plane,
+                    int b_mn, float* C, long long ldc, int M, int N, int K, int epi, const float* bias, int k_slabs,
+                    void* stream) {
+  PGF_CHECK_ARG(A3 && B3 && C, "pgf_gemm_bf16x3: NULL operand");
+  PGF_CHECK_ARG(epi == PGF_EPI_ATOMIC_F32 || epi == PGF_EPI_STORE_F32 || epi == PGF_EPI_BIAS_F32,
+                "pgf_gemm_bf16x3: epilogue %d is not an exact fp32 one (4, 5 or 6)", epi);
+  PGF_CHECK_ARG(epi != PGF_EPI_BIAS_F32 || (bias && aligned16(bias)), "pgf_gemm_bf16x3: epilogue 6 needs a 16-byte aligned bias");
+  PGF_CHECK_ARG((k_slabs > 0) == (epi == PGF_EPI_ATOMIC_F32), "pgf_gemm_bf16x3: k_slabs goes with the accumulating epilogue (4) only");
+  GemmArgs g = {};
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias; g.epi = epi; g.stream_k = k_slabs;
+  // plane pairs, smallest products first (0 = hi, 1 = mid, 2 = lo): (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+  g.nseg = 6;
+  g.seg_a = 2u | (0u << 2) | (1u << 4) | (1u << 6) | (0u << 8) | (0u << 10);
+  g.seg_b = 0u | (2u << 2) | (1u << 4) | (0u << 6) | (1u << 8) | (0u << 10);
+  g.a_plane = a_plane; g.b_plane = b_plane;
+  return gemm_bf16(A3, lda, a_mn, B3, ldb, b_mn, g, static_cast<cudaStream_t>(stream));
+}
+
+int pgf_split3(const float* src, long long ld, int R, int C, const float* bias, int act, const void* mask_plane,
+               long long ld_mask, float* out_f32, long long ld_out, void* planes, long long ldp, long long plane_stride,
+               void* stream) {
+  if (R <= 0 || C <= 0) return PGF_OK;
+  PGF_CHECK_ARG(src && (out_f32 || planes), "pgf_split3: NULL argument");
+  PGF_CHECK_ARG(act >= 0 && act <= 2, "pgf_split3: bad activation %d", act);
+  PGF_CHECK_ARG((C % 8) == 0 && (ld % 4) == 0 && aligned16(src) && (!bias || aligned16(bias)) &&
+                    (!out_f32 || (aligned16(out_f32) && (ld_out % 4) == 0)) &&
+                    (!planes || (aligned16(planes) && (ldp % 8) == 0 && (plane_stride % 8) == 0)) &&
+                    (!mask_plane || (aligned16(mask_plane) && (ld_mask % 8) == 0)),
+                "pgf_split3: C must be a multiple of 8, rows 16-byte aligned");
+  return split3(src, ld, R, C, bias, act, mask_plane, ld_mask, out_f32, ld_out, planes, ldp, plane_stride,
+                static_cast<cudaStream_t>(stream));
+}
+
 int pgf_gemm_partial_rows(int M) { return gemm_partial_rows(M); }
 
 int pgf_reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate, void* stream) {

@@ -11,15 +11,22 @@
 // which is what the weight-gradient GEMMs need (dW = dZ^T . X contracts over the batch) -- the
 // UMMA descriptors read those layouts directly, no transposed copies are ever materialised.
 //
-// Structure (one CTA per SM, persistent, 192 threads):
-//   warp 0     TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB / stage)
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (128x256x16 per instruction)
-//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time -> bias/activation/mask -> global
-// TMEM holds two 128x256 fp32 accumulators (all 512 columns) so the epilogue of tile i overlaps
+// Structure (persistent; one CTA per SM, CTA pairs = clusters of 2 whenever M > 128; 320 threads per CTA):
+//   warp 0     TMA producer: 5-stage ring of {A 128x64, B 128x64 (its half of the pair's 256 columns)} bf16 tiles
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (cta_group::2: 256x256x16 per instruction, leader CTA)
+//   warps 2-9  epilogue, two groups of four warps on alternate column groups: tcgen05.ld -> bias / activation / mask
+//              -> 128B-swizzled shared staging -> TMA store (or TMA fp32 reduce-add)
+// TMEM holds two 128x256 fp32 accumulators per CTA (all 512 columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Work is either whole tiles round-robin, or -- for the K=batch
-// weight-gradient GEMMs whose tile count does not fill 148 SMs -- a stream-K split: the flattened
-// (tile, k-block) space is cut into equal contiguous ranges and partial tiles are combined
-// with fp32 vector reductions into a zero-initialised C.
+// weight-gradient GEMMs whose tile count does not fill 148 SMs -- a split over K slabs (slab-major units),
+// partial tiles combined by TMA fp32 reduce-adds into a zero-initialised C.
+//
+// fp32-parity mode (nseg = 6, pgf_gemm_bf16x3): each fp32 operand is given as three bf16 planes hi/mid/lo with
+// hi+mid+lo == x exactly (pgf_split3); the contraction runs over six plane pairs
+//   (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)      -- smallest terms first
+// as six K segments of ONE accumulation, i.e. every product the fp32 result needs down to 2^-24 relative.  The
+// producer warp walks the segments by moving the plane coordinate of 3-D tensor maps; MMA issuer and epilogue
+// only see six times as many k-blocks.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -109,6 +116,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
   }
 }
@@ -225,26 +246,39 @@ struct WorkUnit {
 //   served to the other tiles from L2 (the weight-gradient GEMMs contract over the batch: K = 65,536,
 //   operands 335 MB each, far larger than L2).  Partial tiles are combined by fp32 reductions.
 struct Scheduler {
-  int num_tiles, kb_total, nslab, worker, nworkers, it;
+  int num_tiles, kb_k, nseg, nslab, tile_major, worker, nworkers, it;
   __device__ Scheduler(const GemmArgs& g, int tile_m, int worker_, int nworkers_) {
     const int mb = (g.M + tile_m - 1) / tile_m, nb = (g.N + BN - 1) / BN;
     num_tiles = mb * nb;
-    kb_total = (g.K + BK - 1) / BK;
+    kb_k = (g.K + BK - 1) / BK;
+    nseg = g.nseg > 1 ? g.nseg : 1;
     nslab = g.stream_k > 0 ? g.stream_k : 1;
+    tile_major = g.tile_major;
     worker = worker_;
     nworkers = nworkers_;
     it = 0;
   }
+  // fp32-parity mode (nseg plane pairs): a slab is a range [a, b) of the ORIGINAL k-blocks and the unit runs all nseg
+  // segments over it, kb0 = a * nseg .. kb1 = b * nseg; k-block kb of the unit is plane pair (kb - kb0) / (b - a) at
+  // original k-block a + (kb - kb0) % (b - a).  The tensor core truncates when it accumulates, an error that grows with
+  // the number of MMAs issued while the accumulator is at full magnitude, i.e. with b - a (the last segment, hi x hi):
+  // slabs bound that chain, and their partial tiles are combined by round-to-nearest fp32 adds.
   __device__ bool next(WorkUnit& u) {
     const long long total = static_cast<long long>(num_tiles) * nslab;
     while (true) {
       const long long unit = worker + static_cast<long long>(it) * nworkers;
       ++it;
       if (unit >= total) return false;
-      const int slab = static_cast<int>(unit / num_tiles);
-      u.tile = static_cast<int>(unit - static_cast<long long>(slab) * num_tiles);
-      u.kb0 = static_cast<int>(static_cast<long long>(kb_total) * slab / nslab);
-      u.kb1 = static_cast<int>(static_cast<long long>(kb_total) * (slab + 1) / nslab);
+      int slab;
+      if (tile_major) {  // the slabs of one tile run back to back: its fp32 partial sums meet in L2 (large C)
+        u.tile = static_cast<int>(unit / nslab);
+        slab = static_cast<int>(unit - static_cast<long long>(u.tile) * nslab);
+      } else {           // slab-major: concurrent units share the K slab of both operands (large operands, small C)
+        slab = static_cast<int>(unit / num_tiles);
+        u.tile = static_cast<int>(unit - static_cast<long long>(slab) * num_tiles);
+      }
+      u.kb0 = static_cast<int>(static_cast<long long>(kb_k) * slab / nslab) * nseg;
+      u.kb1 = static_cast<int>(static_cast<long long>(kb_k) * (slab + 1) / nslab) * nseg;
       if (u.kb1 > u.kb0) return true;  // more slabs than k-blocks: skip the empty ones (all roles agree)
     }
   }
@@ -336,6 +370,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // complete_tx always lands in the phase it belongs to (and a remote arrive.release.cluster per
           // k-block would serialise the peer's producer on a cluster-scope fence).
           if (rank == 0) mbar_expect_tx(fb_local, STAGE_BYTES * CG);
+          if (g.nseg > 1) {
+            // fp32-parity mode: k-block kb of the unit = original k-block a + j % len of plane pair j / len
+            const int len = (u.kb1 - u.kb0) / g.nseg, j = kb - u.kb0;
+            const int seg = j / len, k0 = (u.kb0 / g.nseg + (j - seg * len)) * BK;
+            const int pa = static_cast<int>((g.seg_a >> (2 * seg)) & 3u), pb = static_cast<int>((g.seg_b >> (2 * seg)) & 3u);
+            if (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_3d<CG>(sa + j * 8192, &tmA, fb, m0 + 64 * j, k0, pa);
+            } else {
+              tma_load_3d<CG>(sa, &tmA, fb, k0, m0, pa);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN_CTA / 64; ++j) tma_load_3d<CG>(sb + j * 8192, &tmB, fb, n0 + 64 * j, k0, pb);
+            } else {
+              tma_load_3d<CG>(sb, &tmB, fb, k0, n0, pb);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const int k0 = kb * BK;
           if (A_MN) {
 #pragma unroll
@@ -604,23 +658,26 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D row-major tensor [rows, cols] (cols contiguous, row stride ld elements), box {box_cols, box_rows}, 128B swizzle
+// row-major tensor [planes][rows, cols] (cols contiguous, row stride ld elements, `plane` elements between planes),
+// box {box_cols, box_rows}, 128B swizzle.  planes == 0: plain 2-D map.
 static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
-                     int box_rows, bool f32 = false) {
+                     int box_rows, bool f32 = false, int planes = 0, long long plane = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
     return PGF_ERR_CUDA;
   }
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f32 ? 4 : 2)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  const cuuint64_t esz = f32 ? 4 : 2;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * esz, static_cast<cuuint64_t>(plane) * esz};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, planes > 0 ? 3 : 2,
                         const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", static_cast<int>(r), rows, cols, ld);
+    set_error("pgf_gemm_bf16: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld planes=%d", static_cast<int>(r), rows,
+              cols, ld, planes);
     return PGF_ERR_CUDA;
   }
   return PGF_OK;
@@ -643,6 +700,15 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   }
   CUtensorMap tmA, tmB, tmC;
   int rc;
+  const int planes = g.nseg > 1 ? 3 : 0;
+  if (planes) {
+    if (!out_f32 || g.col_partial || g.nseg > 8 || (g.a_plane % 8) || (g.b_plane % 8)) {
+      set_error("pgf_gemm_bf16x3: fp32-output epilogues only (4, 5, 6), no column partials, plane strides multiples of 8");
+      return PGF_ERR_ARG;
+    }
+  } else {
+    g.nseg = 1;
+  }
   // output staging rows are 128 bytes: 64 bf16 or 32 fp32 columns x 128 accumulator rows per TMA store
   const bool no_c = g.epi == PGF_EPI_DDP_PARTIAL;
   if (no_c) {
@@ -662,7 +728,8 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     }
   }
   // K-major operand [R,K]: box {64 k, BM|BN rows}.  MN-major operand stored [K,R]: box {64 r, 64 k}.
-  rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64) : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM);
+  rc = a_mn ? make_tmap(&tmA, A, g.K, g.M, lda, 64, 64, false, planes, g.a_plane)
+            : make_tmap(&tmA, A, g.M, g.K, lda, BK, BM, false, planes, g.a_plane);
   if (rc != PGF_OK) return rc;
   if (no_c) {
     tmC = tmA;  // never dereferenced
@@ -672,7 +739,8 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   }
   static const bool force_1cta_b = getenv("PGF_GEMM_1CTA") != nullptr;
   const int cg_b = (!force_1cta_b && g.M > BM) ? 2 : 1;
-  rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64) : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN / cg_b);
+  rc = b_mn ? make_tmap(&tmB, B, g.K, g.N, ldb, 64, 64, false, planes, g.b_plane)
+            : make_tmap(&tmB, B, g.N, g.K, ldb, BK, BN / cg_b, false, planes, g.b_plane);
   if (rc != PGF_OK) return rc;
 
   // CTA pairs (cta_group::2) whenever there is at least one full 256-row tile of work per pair
@@ -680,7 +748,7 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   const int cg = (!force_1cta && g.M > BM) ? 2 : 1;
   const int tile_m = BM * cg;
   const int tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
-  const int kb_total = (g.K + BK - 1) / BK;
+  const int kb_k = (g.K + BK - 1) / BK, kb_total = kb_k * g.nseg;
   const int workers_max = num_sms() / cg;
   int workers = tiles < workers_max ? tiles : workers_max;
   if (g.stream_k) {
@@ -689,18 +757,22 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
       return PGF_ERR_ARG;
     }
     // number of K slabs: small enough that one slab of both operands stays L2-resident (<= 64 MB),
-    // then whatever minimises waves x (slab length + epilogue) over the candidates
+    // then whatever minimises waves x (slab length + epilogue) over the candidates.  stream_k > 1: the caller's
+    // count (the fp32-parity mode bounds the length of one TMEM accumulation chain this way).
     const double slab_bytes_per_kb = 2.0 * BK * (static_cast<double>(g.M) + g.N);
     int s_min = static_cast<int>(slab_bytes_per_kb * kb_total / (64.0 * 1024 * 1024)) + 1;
-    if (s_min > kb_total) s_min = kb_total;
+    if (s_min > kb_k) s_min = kb_k;
     int best = s_min;
     double best_cost = 1e300;
-    for (int S = s_min; S <= s_min + 24 && S <= kb_total; ++S) {
+    for (int S = s_min; S <= s_min + 24 && S <= kb_k; ++S) {
       const long long units = static_cast<long long>(tiles) * S;
       const long long waves = (units + workers_max - 1) / workers_max;
       const double cost = static_cast<double>(waves) * (static_cast<double>(kb_total) / S + 4.0);
       if (cost < best_cost) { best_cost = cost; best = S; }
     }
+    if (g.stream_k > 1) best = g.stream_k < kb_k ? g.stream_k : kb_k;
+    // a C far larger than L2 (forward-type GEMMs cut into slabs for accuracy): the slabs of a tile run back to back
+    g.tile_major = static_cast<double>(g.M) * g.N * 4.0 > 48.0 * 1024 * 1024 ? 1 : 0;
     g.stream_k = best;
     const long long units = static_cast<long long>(tiles) * best;
     workers = static_cast<int>(units < workers_max ? units : workers_max);

@@ -14,6 +14,10 @@ Two arithmetic modes:
                     (reference batch size, weight-streaming bound; parity mode, 1e-5)
   precision='bf16'  each model runs the tcgen05 GEMM path (large batch; bf16 operands, fp32
                     accumulate, fp32 master weights + Adam; 2e-2 bar)
+  precision='fp32x3' the same tensor-core GEMMs held to the fp32 bar (1e-5) at large batch: every
+                    fp32 operand enters as three bf16 planes and six plane-pair products are accumulated
+                    (ops.split3 / ops.gemm_bf16x3); precision='fp32' switches to it by itself from
+                    `tc_min_batch` rows on, where the batch is a real dense contraction
 
 Parameter layout per model: one flat fp32 buffer [W1 | b1 | W2 | b2 | Wc | bc | pad] so the
 optimiser is a single launch; `state_dict(i)` / `load_state_dict(i, sd)` use the reference's
@@ -36,7 +40,9 @@ class HeadEngine:
                  noise="philox", betas=(0.9, 0.999), adam_eps=1e-8, dp_init=None):
         if not torch.cuda.is_available():
             raise RuntimeError("HeadEngine needs a CUDA device: there is no CPU fallback")
-        assert precision in ("fp32", "bf16")
+        assert precision in ("fp32", "bf16", "fp32x3")
+        if precision == "fp32x3" and (sum(int(d) for d in feature_dims) % 8 or int(hidden) % 8):
+            raise ValueError("the fp32x3 tensor-core path needs widths that are multiples of 8")
         if precision == "bf16" and sum(int(d) for d in feature_dims) % 128:
             raise ValueError("the bf16 tensor-core path packs the ReLU sign bits in 128-bit rows: the fused width must be a "
                              "multiple of 128 (2304 and 2560 are); use precision='fp32' for other widths")
@@ -77,6 +83,15 @@ class HeadEngine:
         self.DP_m = torch.zeros(self.M, D, device=dev)
         self.DP_v = torch.zeros(self.M, D, device=dev)
         self.shadow = torch.zeros(self.M, self.P, device=dev, dtype=torch.bfloat16) if precision == "bf16" else None
+        # fp32x3: hi/mid/lo bf16 planes of the two GEMM weights (allocated on first use: precision='fp32' only needs them
+        # once a batch of tc_min_batch rows arrives)
+        self.W1p = self.W2p = None
+        self._planes_key = None
+        self.tc_min_batch = 1024      # precision='fp32': batches from this size on take the fp32x3 tensor-core route
+        # fp32x3: 64-wide k-blocks of the contraction per TMEM accumulation chain.  The tensor core truncates when it
+        # accumulates (measured: error grows linearly with the chain, 2.5e-6 rms at 40 k-blocks, below cuBLAS SGEMM's
+        # 9e-7 from ~12 down), so longer contractions are cut into K slabs summed by round-to-nearest fp32 adds.
+        self.x3_chain_kb = 10
         self.t_model = 0
         self.t_dp = 0
         self.fuse_adam = True   # fp32 small-batch path: weight gradients recomputed inside the Adam kernel
@@ -121,6 +136,22 @@ class HeadEngine:
     def sync_shadow(self):
         if self.shadow is not None:
             ops.cast_bf16(self.flat, self.shadow)
+        self._planes_key = None
+
+    def _weight_planes(self):
+        """hi/mid/lo planes of W1 / W2 for the fp32x3 path, refreshed when the weights moved (Adam step, load_state_dict)."""
+        key = self.flat._version          # in-place torch writes; the Adam kernels reset _planes_key themselves
+        if self.W1p is None:
+            bf = torch.bfloat16
+            self.W1p = torch.empty(self.M, 3, self.D, self.D, device=self.device, dtype=bf)
+            self.W2p = torch.empty(self.M, 3, self.H, self.D, device=self.device, dtype=bf)
+        if self._planes_key != key:
+            W1, W2 = self.view("W1"), self.view("W2")
+            for i in range(self.M):
+                ops.split3(W1[i], planes=self.W1p[i])
+                ops.split3(W2[i], planes=self.W2p[i])
+            self._planes_key = key
+        return self.W1p, self.W2p
 
     _KEYS = {"fc_layers.0.weight": "W1", "fc_layers.0.bias": "b1", "fc_layers.2.weight": "W2",
              "fc_layers.2.bias": "b2", "classifier.weight": "Wc", "classifier.bias": "bc"}
@@ -265,6 +296,8 @@ class HeadEngine:
             labels = labels.repeat(n_rep) if labels.dim() == 1 else labels.repeat(1, n_rep)
         W1, b1, W2, b2, Wc, bc = (self.view(n) for n in ("W1", "b1", "W2", "b2", "Wc", "bc"))
         backward = mode != "eval"
+        if self.precision == "fp32x3" or (self.precision == "fp32" and B >= self.tc_min_batch and D % 8 == 0 and H % 8 == 0):
+            return self._pass_x3(blocks, labels, hard, mode, row0, gb, n_rep, B)
         if self.precision == "fp32":
             X = self._buf("X", (M, B, D), torch.float32)
             coef, nspec = self._perturb(blocks, hard, X, row0, n_rep)
@@ -341,6 +374,76 @@ class HeadEngine:
             ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
             ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
         return res
+
+    def _pass_x3(self, blocks, labels, hard, mode, row0, gb, n_rep, B):
+        """One pass on the fp32-parity tensor-core route (models.py:46-51,80 in fp32 arithmetic at large batch): each GEMM
+        contracts hi/mid/lo bf16 planes of BOTH operands (six plane pairs, fp32 accumulate), the elementwise stages between
+        them (bias, ReLU, tanhf, ReLU mask) run in fp32 and emit the next GEMM's planes.  One model at a time: the plane
+        buffers are shared by the models of the engine."""
+        M, D, H = self.M, self.D, self.H
+        bf, f32 = torch.bfloat16, torch.float32
+        b1, b2, Wc, bc = (self.view(n) for n in ("b1", "b2", "Wc", "bc"))
+        W1p, W2p = self._weight_planes()
+        backward = mode != "eval"
+        if mode == "model":
+            ops.fill_zero(self.grad)      # the split-K weight-gradient GEMMs accumulate
+        X = self._buf("X", (M, B, D), f32)
+        coef, nspec = self._perturb(blocks, hard, X, row0, n_rep)
+        X3, H13 = self._buf("X3", (3, B, D), bf), self._buf("H13", (3, B, D), bf)
+        Z1 = self._buf("Z1f", (B, D), f32)
+        H2 = self._buf("H2", (M, B, H), f32)
+        out = self._ce_out(mode, B)
+        if not out:
+            out = dict(logits=torch.empty(M, B, 2, device=self.device), pred=torch.empty(M, B, dtype=torch.int64, device=self.device),
+                       stats=torch.empty(M, 4, device=self.device))
+        chain = max(1, int(self.x3_chain_kb))
+
+        def slabs_of(K):
+            return max(1, round(((K + 63) // 64) / chain))
+
+        def gemm(A3, B3, C, bias=None, **kw):   # forward / input-gradient GEMMs; returns the bias still to be added
+            ns = slabs_of(kw["K"])
+            if ns > 1:
+                ops.fill_zero(C)
+                ops.gemm_bf16x3(A3, B3, C, epi=L.EPI_ATOMIC_F32, k_slabs=ns, **kw)
+                return bias
+            ops.gemm_bf16x3(A3, B3, C, epi=L.EPI_STORE_F32 if bias is None else L.EPI_BIAS_F32, bias=bias, **kw)
+            return None
+
+        for i in range(M):
+            ops.split3(X[i], planes=X3)
+            rb = gemm(X3, W1p[i], Z1, bias=b1[i], M=B, N=D, K=D)
+            ops.split3(Z1, planes=H13, bias=rb, act=L.ACT_RELU)
+            rb = gemm(H13, W2p[i], H2[i], bias=b2[i], M=B, N=H, K=D)
+            ops.split3(H2[i], out=H2[i], bias=rb, act=L.ACT_TANH)
+            lab = labels if labels.dim() == 1 else labels[i]
+            want_dw = mode == "model"
+            res = ops.cls_ce(H2[i], Wc[i], bc[i], lab, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward,
+                             logits=out["logits"][i], pred=out["pred"][i], stats=out["stats"][i],
+                             dz=self._buf("dZ2f", (B, H), f32) if backward else None,
+                             dWc=self.view("Wc", self.grad)[i] if want_dw else None,
+                             dbc=self.view("bc", self.grad)[i] if want_dw else None, want_dw=want_dw,
+                             dz_colsum=self.view("b2", self.grad)[i] if want_dw else None)
+            if not backward:
+                continue
+            dZ23, dZ13 = self._buf("dZ23", (3, B, H), bf), self._buf("dZ13", (3, B, D), bf)
+            ops.split3(res["dz"], planes=dZ23)
+            # dH1 = dZ2 . W2 (B operand stored [K=H, N=D]: MN-major), then the ReLU mask from the sign of H1's hi plane
+            gemm(dZ23, W2p[i], Z1, M=B, N=D, K=H, b_mn=True)
+            ops.split3(Z1, out=Z1, planes=dZ13, mask_plane=H13[0])        # Z1 now holds dZ1 (fp32), dZ13 its planes
+            if mode == "dp":
+                dX = self._buf("dXf", (B, D), f32)
+                gemm(dZ13, W1p[i], dX, M=B, N=D, K=D, b_mn=True)
+                self._dDP_one(i, dX, coef, nspec, row0)
+                continue
+            ops.colsum(Z1, out=self.view("b1", self.grad)[i])
+            slabs = slabs_of(B)
+            # dW = dZ^T . act: both operands stored [K=B, *] (MN-major), K = batch cut into slabs of x3_chain_kb k-blocks
+            ops.gemm_bf16x3(dZ23, H13, self.view("W2", self.grad)[i], M=H, N=D, K=B, a_mn=True, b_mn=True,
+                            epi=L.EPI_ATOMIC_F32, k_slabs=slabs)
+            ops.gemm_bf16x3(dZ13, X3, self.view("W1", self.grad)[i], M=D, N=D, K=B, a_mn=True, b_mn=True,
+                            epi=L.EPI_ATOMIC_F32, k_slabs=slabs)
+        return dict(logits=out["logits"], pred=out["pred"], stats=out["stats"])
 
     # ---- public steps ---------------------------------------------------------------------------
     def train_step(self, blocks, labels, row0=0, global_batch=None, grad_hook=None, dp_pass=True):
@@ -429,6 +532,7 @@ class HeadEngine:
                 grad_hook(self.grad)
             ops.adam_step(self.flat, self.grad, self.m, self.v, self.t_model, self.lr, self.betas, self.adam_eps,
                           bf16_shadow=self.shadow)
+        self._planes_key = None           # the weights moved: the fp32x3 planes are refreshed on their next use
         return self._result(res["stats"])
 
     def _result(self, stats):

@@ -111,12 +111,96 @@ class _HeadMLPFn(torch.autograd.Function):
         return dX, dW1, db1, dW2, db2, dWc, dbc
 
 
+X3_CHAIN_KB = 10   # k-blocks of 64 per TMEM accumulation chain of the fp32x3 GEMMs (see HeadEngine.x3_chain_kb)
+
+
+def _gemm_x3(A3, B3, C, *, K, zeroed=False, **kw):
+    """C = A . B^T on the fp32x3 route, the contraction cut into K slabs of ~X3_CHAIN_KB k-blocks (tensor-core
+    accumulation truncates; slabs are summed by round-to-nearest fp32 adds)."""
+    ns = max(1, round(((K + 63) // 64) / X3_CHAIN_KB))
+    if ns > 1 or zeroed:
+        if not zeroed:
+            ops.fill_zero(C)
+        return ops.gemm_bf16x3(A3, B3, C, K=K, epi=L.EPI_ATOMIC_F32, k_slabs=max(ns, 2) if ns > 1 else 1, **kw)
+    return ops.gemm_bf16x3(A3, B3, C, K=K, epi=L.EPI_STORE_F32, **kw)
+
+
+class _HeadMLPTensorFn(torch.autograd.Function):
+    """fc_layers + classifier (models.py:80-81) with the two dense contractions on the tensor cores, for batches that are a
+    real GEMM.  precision 'fp32x3': fp32 arithmetic (hi/mid/lo bf16 planes of both operands, six plane-pair products, fp32
+    accumulate: the 1e-5 bar); 'bf16': bf16 operands, fp32 accumulate, fused epilogues (the 2e-2 bar).  The 768 -> 2
+    classifier stays on the CUDA-core kernels in fp32 either way."""
+
+    @staticmethod
+    def forward(ctx, X, W1, b1, W2, b2, Wc, bc, precision):
+        X = X.contiguous()
+        B, D = X.shape
+        H = W2.shape[0]
+        dev, bf = X.device, torch.bfloat16
+        exact = precision == "fp32x3"
+        H2 = torch.empty(B, H, device=dev)
+        if exact:
+            mk = lambda t: ops.split3(t.detach().contiguous(), planes=torch.empty(3, *t.shape, device=dev, dtype=bf))
+            Xp, W1p, W2p = mk(X), mk(W1), mk(W2)
+            Z = torch.empty(B, D, device=dev)
+            _gemm_x3(Xp, W1p, Z, M=B, N=D, K=D)
+            H1p = ops.split3(Z, planes=torch.empty(3, B, D, device=dev, dtype=bf), bias=b1.detach(), act=L.ACT_RELU)
+            _gemm_x3(H1p, W2p, H2, M=B, N=H, K=D)
+            ops.split3(H2, out=H2, bias=b2.detach(), act=L.ACT_TANH)
+            aux = Z                          # storage reused for dH1 / dZ1 in backward
+        else:
+            mk = lambda t: ops.cast_bf16(t.detach().contiguous())
+            Xp, W1p, W2p = mk(X), mk(W1), mk(W2)
+            H1p = torch.empty(B, D, device=dev, dtype=bf)
+            aux = torch.empty(B, D // 32, device=dev, dtype=torch.int32)      # ReLU sign bits for the backward mask
+            ops.gemm_bf16(Xp, W1p, H1p, M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1.detach(), aux=aux)
+            ops.gemm_bf16(H1p, W2p, H2, M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2.detach())
+        logits = ops.linear_fwd(H2, Wc.detach(), bc.detach(), L.ACT_NONE)
+        ctx.save_for_backward(Xp, H1p, H2, W1p, W2p, Wc, aux)
+        ctx.exact = exact
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        Xp, H1p, H2, W1p, W2p, Wc, aux = ctx.saved_tensors
+        exact, need = ctx.exact, ctx.needs_input_grad
+        dlogits = dlogits.contiguous()
+        B, H = H2.shape
+        D = Xp.shape[-1]
+        dev, bf = H2.device, torch.bfloat16
+        dWc, dbc = ops.linear_bwd_dw(dlogits, H2)
+        dZ2 = ops.linear_bwd_dx(dlogits, Wc.detach(), mask_src=H2, mask_mode=L.ACT_TANH)
+        db2 = ops.colsum(dZ2)
+        dW2, dW1 = torch.zeros(H, D, device=dev), torch.zeros(D, D, device=dev)
+        dX = torch.empty(B, D, device=dev) if need[0] else None
+        if exact:
+            dZ2p = ops.split3(dZ2, planes=torch.empty(3, B, H, device=dev, dtype=bf))
+            dH1 = aux
+            _gemm_x3(dZ2p, W2p, dH1, M=B, N=D, K=H, b_mn=True)
+            dZ1p = ops.split3(dH1, out=dH1, planes=torch.empty(3, B, D, device=dev, dtype=bf), mask_plane=H1p[0])
+            db1 = ops.colsum(dH1)
+            _gemm_x3(dZ2p, H1p, dW2, M=H, N=D, K=B, a_mn=True, b_mn=True, zeroed=True)
+            _gemm_x3(dZ1p, Xp, dW1, M=D, N=D, K=B, a_mn=True, b_mn=True, zeroed=True)
+            if dX is not None:
+                _gemm_x3(dZ1p, W1p, dX, M=B, N=D, K=D, b_mn=True)
+        else:
+            dZ2p = ops.cast_bf16(dZ2)
+            dZ1p, db1 = torch.empty(B, D, device=dev, dtype=bf), torch.empty(D, device=dev)
+            ops.gemm_bf16(dZ2p, W2p, dZ1p, M=B, N=D, K=H, b_mn=True, epi=L.EPI_BITMASK_BF16, aux=aux, colsum_out=db1)
+            ops.gemm_bf16(dZ2p, H1p, dW2, M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+            ops.gemm_bf16(dZ1p, Xp, dW1, M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+            if dX is not None:
+                ops.gemm_bf16(dZ1p, W1p, dX, M=B, N=D, K=D, b_mn=True, epi=L.EPI_STORE_F32)
+        return dX, dW1, db1, dW2, db2, dWc, dbc, None
+
+
 class ConcatModel(nn.Module):
     """The reference's `ConcatModel` head.  Parameters and their names match the reference so
     `load_state_dict(torch.load('model_dict/<run>/best_f1.pickle'), strict=False)` fills the head."""
 
     def __init__(self, feature_dims=(768, 768, 768), hidden=768, n_class=2, encoder: nn.Module | None = None,
-                 private: bool = True, fixed_formula: bool = True, seed: int = REFERENCE_SEED, tau: float = 1.0):
+                 private: bool = True, fixed_formula: bool = True, seed: int = REFERENCE_SEED, tau: float = 1.0,
+                 precision: str = "fp32", tc_min_batch: int = 1024):
         super().__init__()
         if n_class != 2:
             raise NotImplementedError("the reference classifier is nn.Linear(768, 2)")
@@ -131,6 +215,10 @@ class ConcatModel(nn.Module):
         self.private = private            # False = the reference's model.py with the privacy block commented out
         self.fixed_formula = fixed_formula  # True: past_acc.py:132 ("# fix"); False: model.py:57
         self.tau = tau
+        # arithmetic of the two dense layers: 'fp32' (reference arithmetic: CUDA-core kernels below tc_min_batch rows, the
+        # fp32x3 tensor-core route from there on), 'fp32x3' (always the tensor-core route) or 'bf16' (bf16 GEMM operands)
+        assert precision in ("fp32", "fp32x3", "bf16")
+        self.precision, self.tc_min_batch = precision, int(tc_min_batch)
         self.seed = int(seed)
         self.noise_offset = 0             # one Philox offset per forward: fresh noise every pass
         self.return_gate_index = False
@@ -182,8 +270,14 @@ class ConcatModel(nn.Module):
             else:
                 gated = res
         fc0, fc2 = self.fc_layers[0], self.fc_layers[2]
-        return _HeadMLPFn.apply(gated, fc0.weight, fc0.bias, fc2.weight, fc2.bias, self.classifier.weight,
-                                self.classifier.bias)
+        args = (gated, fc0.weight, fc0.bias, fc2.weight, fc2.bias, self.classifier.weight, self.classifier.bias)
+        D, H = fc0.weight.shape[1], fc2.weight.shape[0]
+        big = gated.shape[0] >= self.tc_min_batch
+        if self.precision == "bf16" and big and D % 128 == 0 and H % 8 == 0:
+            return _HeadMLPTensorFn.apply(*args, "bf16")
+        if D % 8 == 0 and H % 8 == 0 and (self.precision == "fp32x3" or (self.precision == "fp32" and big)):
+            return _HeadMLPTensorFn.apply(*args, "fp32x3")
+        return _HeadMLPFn.apply(*args)
 
 
 def get_model(cfg):

@@ -405,6 +405,37 @@ def gemm_bf16(A, B, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_BF16,
     return C
 
 
+def split3(src, *, planes=None, out=None, bias=None, act=L.ACT_NONE, mask_plane=None):
+    """Elementwise stage of the fp32-parity tensor path: v = act(src + bias) [* (mask_plane > 0)], written as fp32 (`out`,
+    may alias src) and/or as the three bf16 planes [3, R, C] with hi + mid + lo == v exactly (pgf_split3)."""
+    _chk(src, torch.float32, "src")
+    R, Cn = src.shape
+    if planes is not None:
+        _chk(planes, torch.bfloat16, "planes")
+        assert planes.shape == (3, R, Cn) and planes.stride(2) == 1
+    if out is not None:
+        _chk(out, torch.float32, "out")
+    if mask_plane is not None:
+        _chk(mask_plane, torch.bfloat16, "mask_plane")
+    _call(("split3", R, Cn, int(act), int(planes is not None), int(out is not None), int(mask_plane is not None)), "pgf_split3",
+          src.data_ptr(), src.stride(0), R, Cn, _ptr(bias), int(act), _ptr(mask_plane),
+          0 if mask_plane is None else mask_plane.stride(0), _ptr(out), 0 if out is None else out.stride(0), _ptr(planes),
+          0 if planes is None else planes.stride(1), 0 if planes is None else planes.stride(0), _stream())
+    return planes if planes is not None else out
+
+
+def gemm_bf16x3(A3, B3, C, *, M, N, K, a_mn=False, b_mn=False, epi=L.EPI_STORE_F32, bias=None, k_slabs=0):
+    """C[M,N] (fp32) = A . B^T with both operands given as hi/mid/lo bf16 plane triples [3, rows, cols] (ops.split3): the
+    fp32-parity route onto tcgen05 (six plane-pair products in one fp32 accumulation).  k_slabs (EPI_ATOMIC_F32, C zeroed
+    by the caller): 1 = automatic split over K, > 1 = exactly that many slabs."""
+    _chk(A3, torch.bfloat16, "A3"); _chk(B3, torch.bfloat16, "B3"); _chk(C, torch.float32, "C")
+    assert A3.dim() == 3 and B3.dim() == 3 and A3.shape[0] == 3 and B3.shape[0] == 3
+    _call(("gemm_x3", M, N, K, int(a_mn), int(b_mn), epi), "pgf_gemm_bf16x3", A3.data_ptr(), A3.stride(1), A3.stride(0), int(a_mn),
+          B3.data_ptr(), B3.stride(1), B3.stride(0), int(b_mn), C.data_ptr(), C.stride(0), M, N, K, epi, _ptr(bias), int(k_slabs),
+          _stream())
+    return C
+
+
 def gemm_bf16_ddp(A, B, *, M, N, K, b_mn=True, seed, offset, row0, deps_dDP, out, accumulate=False):
     """dDP = deps_dDP * colsum((A . B^T) * Laplace noise): the input-gradient GEMM of fc_layers.0 with the
     dL/dDP reduction fused into its epilogue (the [M,N] product is never written)."""

@@ -153,6 +153,25 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
                   long long ldc, int M, int N, int K, int epi, const float* bias, void* aux,
                   long long ld_aux, int stream_k, float* col_partial, void* stream);
 
+/* ---- (a8, a11) the same GEMMs held to the reference's fp32 arithmetic (north_star's 1e-5 bar) at large batch ----------
+ * replaces: fp32 nn.Linear of fc_layers and its autograd, models.py:46-51,80, when the batch is a real dense contraction
+ *           and bf16 operand rounding (2e-2 bar) is not acceptable.
+ * pgf_split3: the elementwise stage between two such GEMMs.  v = act(src + bias) (act PGF_ACT_*; tanhf, bias optional),
+ *           then v *= (mask_plane > 0) when mask_plane (the hi plane of a ReLU output, bf16 [R, ld_mask]) is given -- the
+ *           ReLU backward of autograd; writes v to out_f32 (optional; may alias src) and/or as three bf16 planes
+ *           hi/mid/lo with hi + mid + lo == v exactly (planes: bf16, plane p at planes + p*plane_stride, row stride ldp).
+ * pgf_gemm_bf16x3: C[M,N] (fp32) = A . B^T with A and B given as such plane triples; six plane-pair products down to
+ *           2^-24 of the result, one fp32 accumulation in TMEM, same kernel and operand layouts (a_mn / b_mn) as
+ *           pgf_gemm_bf16.  epi: PGF_EPI_STORE_F32, PGF_EPI_BIAS_F32, or PGF_EPI_ATOMIC_F32 with k_slabs >= 1 (C zeroed by
+ *           the caller; 1 = the launcher picks the number of K slabs, > 1 = exactly that many: tensor-core accumulation
+ *           truncates, so long contractions are cut into slabs combined by round-to-nearest fp32 adds).            */
+int pgf_split3(const float* src, long long ld, int R, int C, const float* bias, int act, const void* mask_plane,
+               long long ld_mask, float* out_f32, long long ld_out, void* planes, long long ldp, long long plane_stride,
+               void* stream);
+int pgf_gemm_bf16x3(const void* A3, long long lda, long long a_plane, int a_mn, const void* B3, long long ldb,
+                    long long b_plane, int b_mn, float* C, long long ldc, int M, int N, int K, int epi, const float* bias,
+                    int k_slabs, void* stream);
+
 /* Fused bias gradient: with a bf16-output epilogue, col_partial (optional, fp32
  * [pgf_gemm_partial_rows(M)][N]) receives the column sums of the epilogue values of every 32-row
  * accumulator slab (one per epilogue warp); pgf_reduce_partials() sums the slabs in a fixed order:
