@@ -60,6 +60,11 @@ def parse():
     ap.add_argument("--no-pdl", action="store_true", help="sweep48_b8 plan: no programmatic dependent launch")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"],
                     help="sweep_synth64k / dp64k: arithmetic of the dense layers (fp32x3 = fp32 parity on the tensor cores)")
+    ap.add_argument("--dp-overlap", choices=["on", "off"], default="off",
+                    help="dp64k: exchange gradient buckets on a side stream during the backward pass (off: one all-reduce after it; "
+                         "measured faster at 2 GPUs, profiles/r2_dp64k_overlap_n2.txt)")
+    ap.add_argument("--dp-reserve-sms", type=int, default=0, help="dp64k with overlap: SMs the GEMM grids leave to NCCL while a bucket is in flight")
+    ap.add_argument("--dp-chunks", type=int, default=5, help="dp64k: row blocks of the fc_layers.0 weight gradient, one bucket each")
     ap.add_argument("--no-also", action="store_true", help="default workload: skip the secondary measurements in config.also")
     return ap.parse_args()
 
@@ -365,6 +370,59 @@ def measure_fp32x3(dev, world, B, dims, nres=4, K=6, W=3):
     return out
 
 
+def measure_dp64k(dev, rank, world, global_batch, dims, overlap=True, chunks=5, K=30, W=5, nres=4):
+    """BASELINE config 4 at this run's N: ONE model, the global batch of 65,536 split evenly over the ranks, gradients summed
+    by NCCL all-reduce (dDP after pass 1; the weight gradients in buckets overlapped with the backward pass), Adam replicated.
+    Strong scaling: the driver's N = 1, 2, 4, 8 runs of the default line each carry this at their N."""
+    import torch
+    import torch.distributed as dist
+
+    from eeg_multimodal_b200 import HeadEngine, parallel
+
+    B = global_batch // world
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    data = [([torch.rand(B, d, device=dev, generator=g) for d in dims], (torch.rand(B, device=dev, generator=g) < 0.66).long())
+            for _ in range(nres)]
+    eng = HeadEngine(n_models=1, feature_dims=dims, hidden=HIDDEN, eps=1.0, seeds=[980616], precision="bf16", init_seed=980616)
+    eng.fast_replay = True
+    hook = None
+    if world > 1:
+        hook = parallel.OverlappedAllReduce(w1_chunks=chunks, device=dev) if overlap else parallel.make_allreduce_hook()
+
+    def step(i):
+        blocks, labels = data[i % nres]
+        return eng.train_step(blocks, labels, row0=i * global_batch + rank * B, global_batch=global_batch, grad_hook=hook)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    fence()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(K):
+        st = step(W + i)
+    t1.record()
+    fence()
+    ms = torch.tensor([t0.elapsed_time(t1) / K], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    peaks, _ = measured_peaks()
+    D = sum(dims)
+    return {"workload": f"dp64k (BASELINE config 4: one model, global batch {global_batch} = {world} x {B}, D={D})", "n_gpus": world,
+            "value": global_batch / (ms * 1e-3), "unit": "model-samples/s", "ms_per_step": ms, "steps": K, "scaling": "strong",
+            "collective": ("none (1 GPU)" if world == 1 else
+                           f"NCCL all-reduce: dDP {D * 4} B after pass 1 + {eng.P * 4} B of weight gradients per step"
+                           + (f" in {1 + chunks} buckets on a side stream, overlapped with the fc_layers.0 weight-gradient GEMMs" if overlap else " in one call after pass 2")),
+            "step_tensor_frac": flops_per_sample_step(D, HIDDEN) * B / (ms * 1e-3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+            "host_path": "recorded call-plan replay", "loss_last": float(st["loss"][0])}
+
+
 def cpu_reference_leg(args, steps, warmup, sample):
     """The reference's CPU path (oracle restatement incl. the reference's own host noise calls),
     all host threads, on a bounded sample of the workload.  Returns (samples/s, cores, sample str)."""
@@ -522,8 +580,11 @@ def run_ours(args):
     global_batch = B * world if args.workload == "dp64k" else None
     hook = None
     if args.workload == "dp64k" and world > 1:
-        def hook(t):
-            dist.all_reduce(t)
+        if args.dp_overlap == "on":      # buckets exchanged on a side stream under the remaining weight-gradient GEMMs
+            hook = parallel.OverlappedAllReduce(w1_chunks=args.dp_chunks, device=dev, reserve_sms=args.dp_reserve_sms)
+        else:
+            def hook(t):
+                dist.all_reduce(t)
 
     def step(i, join=True):
         blocks, labels = data[i % nres]
@@ -644,6 +705,7 @@ def run_ours(args):
                                                    "hbm_gbs_step", "e2e")}}
 
         also["fp32x3_synth64k"] = measure_fp32x3(dev, world, B, dims, nres=4)
+        also["dp64k"] = measure_dp64k(dev, rank, world, args.batch, dims, overlap=args.dp_overlap == "on", chunks=args.dp_chunks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -659,7 +721,8 @@ def run_ours(args):
                            "l2": (f"{nres} resident batches of {sum(dims) * B * 4 / 1e6:.0f} MB cycled (inputs >> 126 MB L2)" if B >= 4096 else
                                   f"per-step working set = weights + Adam state of {M} models = {M * eng.P * 16 / 1e6:.0f} MB >> 126 MB L2 "
                                   f"(the {sum(dims) * B * 4 / 1e3:.0f} KB batch is not what is streamed)"),
-                           "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else f"dp{world} NCCL all-reduce",
+                           "parallelism": "independent models per GPU, no collective" if args.workload != "dp64k" else
+                           f"dp{world} NCCL all-reduce" + (f", {1 + args.dp_chunks} buckets overlapped with the weight-gradient GEMMs" if isinstance(hook, parallel.OverlappedAllReduce) else ""),
                            "host_path": "recorded call-plan replay" if eng.fast_replay else "python wrappers",
                            "streams": G,
                            "kernel_events": "second pass of K steps (launch-bound workload)" if split_events else "inside the timed region",

@@ -37,6 +37,7 @@ SIGNATURES = {
     "pgf_split3": (I, [P, LL, I, I, P, I, P, LL, P, LL, P, LL, LL, P]),
     "pgf_gemm_bf16x3": (I, [P, LL, LL, I, P, LL, LL, I, P, LL, I, I, I, I, P, I, P]),
     "pgf_gemm_partial_rows": (I, [I]),
+    "pgf_set_sm_reserve": (I, [I]),
     "pgf_reduce_partials": (I, [P, I, I, P, P, I, P]),
     "pgf_gemm_bf16_ddp": (I, [P, LL, P, LL, I, I, I, I, U64, U32, U64, P, P, SZ, P, I, P]),
     "pgf_cls_ce_workspace": (SZ, [I, I, I]),

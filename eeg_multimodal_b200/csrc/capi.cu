@@ -302,6 +302,11 @@ int pgf_split3(const float* src, long long ld, int R, int C, const float* bias, 
 
 int pgf_gemm_partial_rows(int M) { return gemm_partial_rows(M); }
 
+int pgf_set_sm_reserve(int n_sms) {
+  set_sm_reserve(n_sms);
+  return PGF_OK;
+}
+
 int pgf_reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate, void* stream) {
   PGF_CHECK_ARG(partial && out && rows > 0 && N > 0, "pgf_reduce_partials: bad argument");
   return reduce_partials(partial, rows, N, coef, out, accumulate, static_cast<cudaStream_t>(stream));

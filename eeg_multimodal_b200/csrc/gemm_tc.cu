@@ -683,6 +683,12 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
   return PGF_OK;
 }
 
+// SMs the persistent GEMM grids leave free (pgf_set_sm_reserve): while a collective is in flight on another stream its
+// kernels need SMs of their own -- a one-CTA-per-SM grid that does not fit next to them has its last clusters wait for
+// the first ones to finish, which costs far more than the SMs given up.
+static thread_local int g_sm_reserve = 0;
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
+
 int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, const GemmArgs& g_in,
               cudaStream_t s) {
   GemmArgs g = g_in;
@@ -749,7 +755,8 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
   const int tile_m = BM * cg;
   const int tiles = ((g.M + tile_m - 1) / tile_m) * ((g.N + BN - 1) / BN);
   const int kb_k = (g.K + BK - 1) / BK, kb_total = kb_k * g.nseg;
-  const int workers_max = num_sms() / cg;
+  const int sms_usable = num_sms() - g_sm_reserve > 2 * cg ? num_sms() - g_sm_reserve : 2 * cg;
+  const int workers_max = sms_usable / cg;
   int workers = tiles < workers_max ? tiles : workers_max;
   if (g.stream_k) {
     if (g.epi != PGF_EPI_ATOMIC_F32) {

@@ -100,6 +100,7 @@ class HeadEngine:
         self.noise_offset = 0
         self._bufs = {}
         self._injected = None
+        self._bucket_hook = None      # set for the duration of a data-parallel step whose grad_hook exchanges buckets
         self._coef_key = None
         self.exp_eps_dev = torch.tensor(self.exp_eps, dtype=torch.float32, device=dev)
         # arbitrary per-model seeds: a device array read by the grouped kernels (one launch for the whole sweep)
@@ -369,10 +370,25 @@ class HeadEngine:
                     self._dDP_one(i, dX, coef, nspec, row0)
             return res
         gW1, gW2 = self.view("W1", self.grad), self.view("W2", self.grad)
+        bucket = self._bucket_hook
+        off_tail = self.layout["b1"][0]
         for i in range(M):
             # dW = dZ^T . act: both operands are stored [K=B, *] -> MN-major, K = batch, split-K
             ops.gemm_bf16(dZ2[i], H1[i], gW2[i], M=H, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
-            ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+            if bucket is None:
+                ops.gemm_bf16(dZ1[i], X[i], gW1[i], M=D, N=D, K=B, a_mn=True, b_mn=True, epi=L.EPI_ATOMIC_F32, stream_k=True)
+                continue
+            # data-parallel mode: everything but fc_layers.0.weight is final (b1 from the dZ1 epilogue, b2 / Wc / bc from
+            # cls_ce, W2 just queued) and travels while the fc_layers.0 weight gradient is computed in row blocks, each
+            # block's exchange running under the next block's GEMM (parallel.OverlappedAllReduce)
+            self._bucket(bucket, i * self.P + off_tail, self.P - off_tail)
+            nchunk = max(1, min(int(bucket.w1_chunks), D // 256))
+            rows = -(-D // nchunk // 8) * 8
+            for r0 in range(0, D, rows):
+                r1 = min(D, r0 + rows)
+                ops.gemm_bf16(dZ1[i][:, r0:r1], X[i], gW1[i][r0:r1], M=r1 - r0, N=D, K=B, a_mn=True, b_mn=True,
+                              epi=L.EPI_ATOMIC_F32, stream_k=True)
+                self._bucket(bucket, i * self.P + self.layout["W1"][0] + r0 * D, (r1 - r0) * D)
         return res
 
     def _pass_x3(self, blocks, labels, hard, mode, row0, gb, n_rep, B):
@@ -445,6 +461,12 @@ class HeadEngine:
                             epi=L.EPI_ATOMIC_F32, k_slabs=slabs)
         return dict(logits=out["logits"], pred=out["pred"], stats=out["stats"])
 
+    def _bucket(self, hook, off, n):
+        """A finished slice [off, off+n) of the flat gradient buffer goes to the data-parallel exchange."""
+        if ops.RECORD is not None:
+            ops.RECORD.append((("hook",), None, ("bucket", off, n)))
+        hook.bucket(self.grad.view(-1)[off:off + n])
+
     # ---- public steps ---------------------------------------------------------------------------
     def train_step(self, blocks, labels, row0=0, global_batch=None, grad_hook=None, dp_pass=True):
         """One reference step (past_acc.py:198-212) for every model.  `blocks`: list of [B,Di]
@@ -479,7 +501,13 @@ class HeadEngine:
             if ok:
                 hook = None
                 if grad_hook is not None:
-                    hook = lambda which: grad_hook(self.dDP if which == "dDP" else self.grad)
+                    def hook(which, off=0, n=0):
+                        if which == "bucket":
+                            grad_hook.bucket(self.grad.view(-1)[off:off + n])
+                        elif which == "finish":
+                            grad_hook.finish()
+                        else:
+                            grad_hook(self.dDP if which == "dDP" else self.grad)
                 ent["plan"].replay(n, inputs, hook)
                 self.noise_offset += d[0]
                 self.t_dp += d[1]
@@ -523,10 +551,19 @@ class HeadEngine:
             self.t_dp += 1
             ops.adam_step(self.DP, self.dDP, self.DP_m, self.DP_v, self.t_dp, self.lr, self.betas, self.adam_eps)
         self.t_model += 1
-        res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch,
-                         fuse_adam=grad_hook is None and self.fuse_adam)
+        bucketed = grad_hook is not None and getattr(grad_hook, "bucketed", False) and self.precision == "bf16"
+        self._bucket_hook = grad_hook if bucketed else None
+        try:
+            res = self._pass(blocks, labels, hard=True, mode="model", row0=row0, global_batch=global_batch,
+                             fuse_adam=grad_hook is None and self.fuse_adam)
+        finally:
+            self._bucket_hook = None
         if not res.get("adam_done"):
-            if grad_hook is not None:
+            if bucketed:          # every slice is already travelling: wait for the last one
+                if ops.RECORD is not None:
+                    ops.RECORD.append((("hook",), None, ("finish",)))
+                grad_hook.finish()
+            elif grad_hook is not None:
                 if ops.RECORD is not None:
                     ops.RECORD.append((("hook",), None, ("grad",)))
                 grad_hook(self.grad)

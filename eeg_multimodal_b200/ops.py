@@ -160,7 +160,7 @@ class CallPlan:
         lib = L.load()
         for tag, name, fn, base, dyn, sub, _ in self.calls:
             if name is None:
-                hook(base[0])
+                hook(*base)
                 continue
             args = base
             if dyn or sub:

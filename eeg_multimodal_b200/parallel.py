@@ -68,6 +68,59 @@ def make_allreduce_hook(group=None):
     return hook
 
 
+class OverlappedAllReduce:
+    """grad_hook for HeadEngine.train_step in the data-parallel mode that overlaps the
+    gradient exchange with the backward pass instead of running one all-reduce after it.
+
+    The engine calls `bucket(t)` right after it has ENQUEUED the kernels that complete the gradient slice `t` (a
+    contiguous 1-D view of its flat gradient buffer): first everything but fc_layers.0.weight -- final once the
+    fc_layers.2 weight-gradient GEMM is queued -- then fc_layers.0.weight in `w1_chunks` row blocks, each produced by its
+    own split-K GEMM launch.  Every bucket is summed over ranks on a side stream that waits for exactly those kernels,
+    so its transfer runs under the GEMMs of the next bucket; `finish()` (before Adam) makes the compute stream wait for
+    the last one.  Called as a plain function (`hook(t)`) it is the blocking all-reduce -- the engine uses that for
+    dDP, whose 10 KB are needed by the next kernel.  Sums of fp32 in NCCL's fixed ring/tree order: the bucketing
+    changes which elements travel together, not the value any element gets, so results equal the single all-reduce."""
+
+    bucketed = True
+
+    def __init__(self, group=None, w1_chunks=5, device=None, reserve_sms=0):
+        self.group = group
+        self.w1_chunks = int(w1_chunks)
+        self.reserve_sms = int(reserve_sms)   # SMs the GEMM grids leave to the collective while a bucket is in flight
+        self.active = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
+        self.comm = torch.cuda.Stream(device=device) if self.cuda else None
+        self._pending = False
+        self.n_buckets = 0
+
+    def __call__(self, t: torch.Tensor):
+        if self.active:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def bucket(self, t: torch.Tensor):
+        self.n_buckets += 1
+        if not self.active:
+            return
+        if self.comm is None:          # CPU / gloo (tests): no streams to overlap on
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        if self.reserve_sms and not self._pending:
+            from . import _lib
+            _lib.load().pgf_set_sm_reserve(self.reserve_sms)
+        self._pending = True
+
+    def finish(self):
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.comm)
+            self._pending = False
+            if self.reserve_sms:
+                from . import _lib
+                _lib.load().pgf_set_sm_reserve(0)
+
+
 def gather_metrics(local: dict, group=None):
     """Host-side gather of per-model metrics {model_index: value} from all ranks (epoch end)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -178,6 +178,10 @@ int pgf_gemm_bf16x3(const void* A3, long long lda, long long a_plane, int a_mn, 
  *   out[n] = (coef ? coef[n] : 1) * sum_r partial[r][n]      (+= if accumulate)
  * replaces: the `.sum(0)` of autograd's nn.Linear bias gradient (fc_layers.0.bias).              */
 int pgf_gemm_partial_rows(int M);
+/* SMs the persistent GEMM grids launched by THIS thread leave free from now on (0 = none; default).  The data-parallel
+ * mode sets it while a gradient bucket is being all-reduced on a side stream, so that the collective's kernels and the
+ * one-CTA-per-SM GEMM grid are co-resident instead of queueing behind each other. */
+int pgf_set_sm_reserve(int n_sms);
 int pgf_reduce_partials(const float* partial, int rows, int N, const float* coef, float* out, int accumulate,
                         void* stream);
 

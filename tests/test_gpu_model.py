@@ -371,3 +371,40 @@ def test_streamed_ensemble_is_bit_identical_to_sequential_engines(dev):
             assert torch.equal(a.flat, b.flat) and torch.equal(a.DP, b.DP)
         ev = ens.eval_step(blocks, labels)
         assert ev["pred"].shape[0] == 6 and ev["logits"].shape[:2] == (6, 8)
+
+
+def test_engine_bucketed_gradient_exchange_points(dev):
+    """Data-parallel mode: the engine hands its gradient to the exchange hook in buckets -- everything but
+    fc_layers.0.weight once the fc_layers.2 weight gradient is queued, then fc_layers.0.weight in row blocks each computed
+    by its own split-K launch -- and the step, wrapper path or recorded call plan, matches the unbucketed step."""
+    from eeg_multimodal_b200 import HeadEngine, parallel
+
+    B, dims = 1024, (2048, 512)
+    g = torch.Generator().manual_seed(3)
+    blocks = [torch.rand(B, d, generator=g).to(dev) for d in dims]
+    label = (torch.rand(B, generator=g) < 0.66).long().to(dev)
+    engs = [HeadEngine(n_models=1, feature_dims=dims, eps=1.0, lr=1e-6, precision="bf16") for _ in range(3)]
+    engs[2].fast_replay = True
+    seen = []
+
+    class Spy(parallel.OverlappedAllReduce):
+        def bucket(self, t):
+            seen.append((t.data_ptr(), t.numel()))
+            super().bucket(t)
+
+    hooks = [None, Spy(w1_chunks=4), parallel.OverlappedAllReduce(w1_chunks=4)]
+    for _ in range(4):
+        for e, h in zip(engs, hooks):
+            st = e.train_step(blocks, label, global_batch=B, grad_hook=h)
+    torch.cuda.synchronize()
+    e1 = engs[1]
+    per_step = seen[-5:]
+    base, P, Dd = e1.grad.data_ptr(), e1.P, 2560
+    assert per_step[0] == (base + 4 * e1.layout["b1"][0], P - e1.layout["b1"][0])               # [b1 | W2 | b2 | Wc | bc]
+    assert [n for _, n in per_step[1:]] == [640 * Dd] * 4 and [p for p, _ in per_step[1:]] == [base + 4 * 640 * Dd * c for c in range(4)]
+    assert hooks[2].n_buckets == 20                                                              # replayed plans reach the hook too
+    for e in engs[1:]:
+        assert rel_err(e.grad, engs[0].grad) < 1e-5 and rel_err(e.dDP, engs[0].dDP) < 1e-5
+        d = (e.flat - engs[0].flat).abs()
+        assert float(d.max()) <= 8.2e-6 and float((d > 2e-8).float().mean()) < 2e-3
+    assert torch.equal(engs[1].grad, engs[2].grad) and torch.equal(engs[1].flat, engs[2].flat)   # plan replay == wrapper path

@@ -48,8 +48,16 @@ def _worker(rank, world, port, out_dir):
     lo, hi = parallel.batch_slice(GB, world, rank)
     mine = _grads([b[lo:hi] for b in blocks], label[lo:hi], p, lap[lo:hi], gum[:, lo:hi], 1.0 / GB)
     hook = parallel.make_allreduce_hook()
+    bucketed = mine.clone()
     hook(mine)
     err = float((mine - full).abs().max() / full.abs().max())
+    # the same exchange in buckets (what the data-parallel GPU step does while the backward pass is still running)
+    ov = parallel.OverlappedAllReduce(w1_chunks=3)
+    k = bucketed.numel() // 3
+    for a, b in ((2 * k, bucketed.numel()), (0, k), (k, 2 * k)):
+        ov.bucket(bucketed[a:b])
+    ov.finish()
+    assert ov.active and ov.n_buckets == 3 and torch.equal(bucketed, mine)
     # sweep mode: disjoint ownership, metrics gathered on every rank
     own = parallel.shard_models(5, world, rank)
     merged = parallel.gather_metrics({m: 0.9 + 0.01 * m for m in own})
