@@ -454,7 +454,13 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "model-samples/sec", "value": v, "unit": "model-samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "reference CPU path; bounded sample of the same workload"},
+            "config": {"workload": args.workload, "models_per_gpu": args.models_per_gpu, "models_total": args.models_per_gpu * args.gpus,
+                       "batch_per_model": args.batch, "feature_dims": list(DIMS), "hidden": HIDDEN,
+                       "step": "reference two-pass step incl. both Adam updates",
+                       "sample": f"each timed step = ONE model of that workload on {args.cpu_sample} of its {args.batch} samples per batch "
+                                 "(fp32, torch CPU, all host threads); every model and every sample costs the same, so model-samples/s "
+                                 "of the bounded sample IS the workload's rate (a full 6 x 65,536 step takes minutes on the host)",
+                       "parallelism": "single process, all host cores"},
             "cpu_baseline": {"value": v, "unit": "model-samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "model-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -94,6 +94,10 @@ class HeadEngine:
         self.x3_chain_kb = 10
         self.t_model = 0
         self.t_dp = 0
+        # bf16 path: True stores the Tanh output H2 [B,768] as bf16 as well.  Measured at B=65,536 (6 models): the
+        # fc_layers.2 GEMM gains 3 % (0.241 -> 0.233 ms), cls_ce pass 2 -- issue-bound, not byte-bound -- loses 9 %
+        # (0.465 -> 0.508 ms): +0.2 % on the step, so H2 stays fp32 (exact classifier / loss arithmetic) by default.
+        self.h2_bf16 = False
         self.fuse_adam = True   # fp32 small-batch path: weight gradients recomputed inside the Adam kernel
         self.fast_replay = False  # launch-bound regimes: replay recorded C-ABI call plans (see _train_step_planned)
         self._plans = {}
@@ -334,14 +338,15 @@ class HeadEngine:
         X = self._buf("Xh", (M, B, D), bf)
         coef, nspec = self._perturb(blocks, hard, X, row0, n_rep)
         H1 = self._buf("H1h", (M, B, D), bf)
-        H2 = self._buf("H2f", (M, B, H), torch.float32)  # tanh output kept in fp32: exact logits / loss
+        h2b = bool(self.h2_bf16)
+        H2 = self._buf("H2h", (M, B, H), bf) if h2b else self._buf("H2f", (M, B, H), torch.float32)
         W1h, W2h = self.view("W1", self.shadow), self.view("W2", self.shadow)
         # ReLU sign bits (1 bit per activation) for the backward mask
         bits = self._buf("relu_bits", (M, B, D // 32), torch.int32) if backward else None
         for i in range(M):
             ops.gemm_bf16(X[i], W1h[i], H1[i], M=B, N=D, K=D, epi=L.EPI_BIAS_RELU_BF16, bias=b1[i],
                           aux=None if bits is None else bits[i])
-            ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_F32, bias=b2[i])
+            ops.gemm_bf16(H1[i], W2h[i], H2[i], M=B, N=H, K=D, epi=L.EPI_BIAS_TANH_BF16 if h2b else L.EPI_BIAS_TANH_F32, bias=b2[i])
         res = ops.cls_ce(H2, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / gb, backward=backward, **self._ce_out(mode, B),
                          dz=self._buf("dZ2h", (M, B, H), bf) if backward else None, dz_dtype=bf,
                          dWc=self.view("Wc", self.grad) if mode == "model" else None,

@@ -247,10 +247,11 @@ def _q(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def head_fwd_bwd_bf16sim(blocks, p: HeadParams, epsilon, lap_noise, fixed: bool = True, grad_scale=None):
+def head_fwd_bwd_bf16sim(blocks, p: HeadParams, epsilon, lap_noise, fixed: bool = True, grad_scale=None,
+                         h2_bf16: bool = False):
     """models.py:69-82 + cal_loss + autograd, restated with bf16 rounding at exactly the points where
     the B200 bf16 path stores bf16 (perturbed features X, weights W1/W2, ReLU output H1, dZ2, dZ1);
-    everything else (accumulation, Tanh output H2, logits, loss, dX, all weight gradients) is fp32.
+    everything else (accumulation, Tanh output H2 unless h2_bf16, logits, loss, dX, all weight gradients) is fp32.
     The Gumbel gate is the identity (hard) / within 1 ulp (soft), see gumbel_mask, and is skipped.
     Needed because a ReLU network's gradient is discontinuous in its inputs: rounding X and W to
     bf16 flips the sign of a fraction p of pre-activations, which moves dZ1 by ~sqrt(p) in Frobenius
@@ -265,6 +266,8 @@ def head_fwd_bwd_bf16sim(blocks, p: HeadParams, epsilon, lap_noise, fixed: bool 
     W1q, W2q = _q(p.W1.detach()), _q(p.W2.detach())
     H1 = _q(F.linear(X, W1q, p.b1.detach()).relu())
     H2 = F.linear(H1, W2q, p.b2.detach()).tanh()
+    if h2_bf16:                      # HeadEngine.h2_bf16: the Tanh output is stored as bf16 too
+        H2 = _q(H2)
     logits = F.linear(H2, p.Wc.detach(), p.bc.detach())
 
     def backward(label):

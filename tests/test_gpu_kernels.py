@@ -673,3 +673,29 @@ def test_no_out_of_bounds_writes_at_ragged_sizes(dev):
     torch.cuda.synchronize()
     for c in checks:
         c()
+
+
+def test_cls_ce_exact_tie_takes_the_first_index(dev):
+    """torch.argmax returns the first maximal index (base_train.py:63): with both classifier rows and biases equal every
+    logit pair ties EXACTLY, so every prediction must be class 0, accuracy the share of label 0, and the softmax gradient
+    (0.5 - onehot) / B -- on the fp32 and on the bf16-activation path, at the reference batch and at a large one."""
+    from eeg_multimodal_b200 import ops
+
+    for B, dt in ((8, torch.float32), (8, torch.bfloat16), (601, torch.float32), (4096, torch.bfloat16)):
+        g = torch.Generator().manual_seed(B)
+        h = torch.tanh(torch.randn(B, 768, generator=g)).to(dev).to(dt)
+        row = torch.randn(768, generator=g) * 0.05
+        Wc = torch.stack([row, row]).to(dev)
+        bc = torch.tensor([0.25, 0.25], device=dev)
+        labels = (torch.rand(B, generator=g) < 0.66).long().to(dev)
+        res = ops.cls_ce(h, Wc, bc, labels, loss_scale=1.0 / B, grad_scale=1.0 / B, backward=True, dz_dtype=dt)
+        logits = res["logits"].cpu()
+        assert torch.equal(logits[:, 0], logits[:, 1])                     # the tie is exact, not approximate
+        assert int(res["pred"].abs().sum()) == 0                            # first index wins
+        st = res["stats"].cpu()
+        n0 = int((labels == 0).sum())
+        assert float(st[1]) == n0 and abs(float(st[2]) - n0 / B) < 1e-7
+        assert abs(float(st[0]) - 0.6931471805599453) < 1e-6                # mean CE of a 50/50 prediction = ln 2
+        assert float(res["dbc"].cpu().sum().abs()) < 1e-6                   # softmax rows sum to one: dbc[0] + dbc[1] == 0
+        exp_dbc0 = (0.5 * B - n0) / B
+        assert abs(float(res["dbc"][0]) - exp_dbc0) < 1e-6

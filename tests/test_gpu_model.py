@@ -206,8 +206,9 @@ def test_engine_train_step_philox_learns(dev):
     assert ev["pred"].shape == (2, B) and bool((ev["acc"] >= 0.9).all())
 
 
+@pytest.mark.parametrize("h2_bf16", [True, False])
 @pytest.mark.parametrize("B", [256, 1000])
-def test_engine_bf16_tensor_core_path_matches_oracle(dev, B):
+def test_engine_bf16_tensor_core_path_matches_oracle(dev, B, h2_bf16):
     """bf16 GEMM inputs, fp32 accumulate: logits/loss/gradients within 2e-2 of the fp32 oracle."""
     from eeg_multimodal_b200 import HeadEngine
 
@@ -216,6 +217,7 @@ def test_engine_bf16_tensor_core_path_matches_oracle(dev, B):
     blocks = [torch.rand(B, d, generator=g) for d in dims]
     label = (torch.rand(B, 1, generator=g) < 0.66).long()
     eng = HeadEngine(n_models=1, feature_dims=dims, eps=1.0, lr=1e-3, precision="bf16")
+    eng.h2_bf16 = h2_bf16
     p = ho.make_params(Dd, H, seed=5, dp=(torch.randn(Dd, generator=g) * 0.1).numpy())
     eng.load_state_dict(0, {"fc_layers.0.weight": p.W1, "fc_layers.0.bias": p.b1, "fc_layers.2.weight": p.W2,
                             "fc_layers.2.bias": p.b2, "classifier.weight": p.Wc, "classifier.bias": p.bc, "DP": p.DP}, strict=True)
@@ -223,7 +225,7 @@ def test_engine_bf16_tensor_core_path_matches_oracle(dev, B):
     db, lab = [b.to(dev) for b in blocks], eng._labels(label.to(dev))
     cos = lambda a, b: float(torch.nn.functional.cosine_similarity(a.detach().cpu().double().flatten(), b.detach().double().flatten(), dim=0))
     # oracle with the same bf16 rounding points as the kernels (see head_fwd_bwd_bf16sim)
-    logits_q, backward_q = ho.head_fwd_bwd_bf16sim(blocks, p, 1.0, lap)
+    logits_q, backward_q = ho.head_fwd_bwd_bf16sim(blocks, p, 1.0, lap, h2_bf16=h2_bf16)
     gq = backward_q(label)
     for mode, hard in (("dp", False), ("model", True)):
         po = p.clone(requires_grad=True)
