@@ -65,6 +65,13 @@ def parse():
                          "measured faster at 2 GPUs, profiles/r2_dp64k_overlap_n2.txt)")
     ap.add_argument("--dp-reserve-sms", type=int, default=0, help="dp64k with overlap: SMs the GEMM grids leave to NCCL while a bucket is in flight")
     ap.add_argument("--dp-chunks", type=int, default=5, help="dp64k: row blocks of the fc_layers.0 weight gradient, one bucket each")
+    ap.add_argument("--fanout", choices=["auto", "on", "off"], default="auto",
+                    help="sweep_synth64k at N > 1, end-to-end leg: upload 1/N of the shared batch per GPU and exchange the slices over "
+                         "NVLink.  auto = from 8 GPUs on, where eight full uploads saturate the host link (measured at 2 GPUs: 0.96 "
+                         "of the HBM-resident rate with the exchange against 0.98 with plain per-GPU uploads)")
+    ap.add_argument("--fanout-mode", choices=["p2p", "nccl"], default="nccl", help="transport of the fan-out (parallel.SharedBatchFanout)")
+    ap.add_argument("--fanout-reserve", type=int, default=None, help="SMs the GEMM grids leave free during the fan-out (default: the transport's own)")
+    ap.add_argument("--fanout-ctas", type=int, default=8, help="CTAs of the fan-out communicator (= SMs the GEMM grids leave free)")
     ap.add_argument("--no-also", action="store_true", help="default workload: skip the secondary measurements in config.also")
     return ap.parse_args()
 
@@ -656,20 +663,31 @@ def run_ours(args):
     # ---- end to end through the public API: host (pinned) buffers, H2D per step, D2H of the losses
     e2e = None
     if not args.no_e2e:
-        host = [([torch.rand(B, d).pin_memory() for d in dims], (torch.rand(B) < 0.66).long().pin_memory()) for _ in range(2)]
+        # The sweep's models read the same dataset in the same order on every GPU (the reference runs them all over one
+        # DataLoader with one seed), so at N > 1 the batch crosses the host link once per NODE: rank r uploads rows
+        # [r*B/N, (r+1)*B/N) and the slices are exchanged over NVLink (parallel.SharedBatchFanout).
+        fan = None
+        if world > 1 and args.workload == "sweep_synth64k" and B % world == 0 and (args.fanout == "on" or (args.fanout == "auto" and world >= 8)):
+            fan = parallel.SharedBatchFanout(B, dev, mode=args.fanout_mode, max_ctas=args.fanout_ctas, reserve_sms=args.fanout_reserve)
+        hrows = B // world if fan is not None else B
+        host = [([torch.rand(hrows, d).pin_memory() for d in dims], (torch.rand(hrows) < 0.66).long().pin_memory()) for _ in range(2)]
         devbuf = [([torch.empty(B, d, device=dev) for d in dims], torch.empty(B, dtype=torch.int64, device=dev)) for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
         loss_host = torch.empty(M, 4).pin_memory()
+        fan_mode = fan.register({s: [*devbuf[s][0], devbuf[s][1]] for s in range(2)}) if fan is not None else None
 
         def upload(i):
             s = i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[s])
-                for hb, db in zip(host[s][0], devbuf[s][0]):
-                    db.copy_(hb, non_blocking=True)
-                devbuf[s][1].copy_(host[s][1], non_blocking=True)
+                if fan is not None:
+                    fan.upload(s, [*host[s][0], host[s][1]])
+                else:
+                    for hb, db in zip(host[s][0], devbuf[s][0]):
+                        db.copy_(hb, non_blocking=True)
+                    devbuf[s][1].copy_(host[s][1], non_blocking=True)
                 ready[s].record(copy_stream)
 
         def e2e_loop(n, first):
@@ -696,9 +714,16 @@ def run_ours(args):
         ems = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        h2d = sum(B * d * 4 for d in dims) + B * 8
-        e2e = {"value": samples_per_step * K / (float(ems) * 1e-3), "unit": "model-samples/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": M * 4 * 4, "ms_per_step": float(ems) / K}
+        h2d = sum(hrows * d * 4 for d in dims) + hrows * 8          # per GPU
+        e2e = {"value": samples_per_step * K / (float(ems) * 1e-3), "unit": "model-samples/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": M * 4 * 4 * world, "ms_per_step": float(ems) / K, "h2d_bytes_per_step_per_gpu": h2d,
+               "input_path": ("pinned host -> H2D of the whole batch on every GPU" if fan is None else
+                              f"pinned host -> H2D of 1/{world} of the shared batch per GPU -> " +
+                              ("pushed into every peer's buffer over NVLink by the copy engines (CUDA IPC mappings)" if fan_mode == "p2p" else
+                               f"NCCL all-gather over NVLink on the copy stream ({args.fanout_ctas}-CTA communicator)") +
+                              f"; the GEMM grids leave {fan.reserve_sms} SMs free")}
+        if fan is not None:
+            fan.close()
 
     # ---- secondary measurements carried in config.also: BASELINE config 3 as written (fp32, D=2304, B=8, 6 models per GPU)
     also = None

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pgf_adam_step_strided": (I, [P, P, P, P, P, LL, LL, I, I, F, F, F, F, F, P]),
     "pgf_linear_adam_step": (I, [P, LL, LL, P, LL, LL, I, I, I, P, P, P, P, P, P, LL, I, F, F, F, F, F, I, P]),
     "pgf_fill_zero": (I, [P, SZ, P]),
+    "pgf_memcpy_peer_async": (I, [P, I, P, I, SZ, P]),
     "pgf_cast_f32_to_bf16": (I, [P, P, LL, P]),
     "pgf_colsum_workspace": (SZ, [I, I]),
     "pgf_colsum": (I, [P, I, LL, I, I, P, P, SZ, P]),
@@ -99,7 +100,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful call (for the bench's `gpu_launches` count)
-LAUNCHES_PER_CALL = {"pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
+LAUNCHES_PER_CALL = {"pgf_memcpy_peer_async": 0, "pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
 launch_count = 0
 launch_by_name = {}
 

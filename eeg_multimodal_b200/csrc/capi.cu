@@ -392,6 +392,26 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
   return linear_adam_step(a, n_models, static_cast<cudaStream_t>(stream));
 }
 
+int pgf_memcpy_peer_async(void* dst, int dst_device, const void* src, int src_device, size_t nbytes, void* stream) {
+  if (nbytes == 0) return PGF_OK;
+  PGF_CHECK_ARG(dst && src, "pgf_memcpy_peer_async: NULL pointer");
+  if (dst_device != src_device) {
+    int cur = -1, can = 0;
+    PGF_CUDA_CALL(cudaGetDevice(&cur));
+    const int other = cur == src_device ? dst_device : src_device;
+    PGF_CUDA_CALL(cudaDeviceCanAccessPeer(&can, cur, other));
+    PGF_CHECK_ARG(can, "pgf_memcpy_peer_async: device %d cannot access device %d directly", cur, other);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(other, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      set_error("pgf_memcpy_peer_async: cudaDeviceEnablePeerAccess(%d) failed: %s", other, cudaGetErrorString(e));
+      return PGF_ERR_CUDA;
+    }
+    (void)cudaGetLastError();   // clear the sticky 'already enabled'
+  }
+  PGF_CUDA_CALL(cudaMemcpyPeerAsync(dst, dst_device, src, src_device, nbytes, static_cast<cudaStream_t>(stream)));
+  return PGF_OK;
+}
+
 int pgf_fill_zero(void* p, size_t nbytes, void* stream) {
   if (nbytes == 0) return PGF_OK;
   PGF_CHECK_ARG(p, "pgf_fill_zero: NULL pointer");

@@ -121,6 +121,148 @@ class OverlappedAllReduce:
                 _lib.load().pgf_set_sm_reserve(0)
 
 
+class SharedBatchFanout:
+    """The batch of a sweep step crosses the host link ONCE per node instead of once per GPU.
+
+    Every model of the eps x seed sweep reads the same dataset in the same order (the reference runs all of them with one
+    seed over one DataLoader, compare_privacy_budget.py:50-62), so with the models sharded over the GPUs of a box every
+    rank used to upload the same batch: eight concurrent 671 MB copies per step saturate the host side and cost 12 % of the
+    8-GPU end-to-end rate.  Here rank r uploads rows [r*B/N, (r+1)*B/N) from its pinned host slice and the slices are
+    exchanged over NVLink, under the previous step's GEMMs.  Two transports:
+
+    mode='nccl'  (default) in-place NCCL all-gather on a communicator of its own limited to `max_ctas` CTAs, with the GEMM
+                 grids leaving that many SMs free (pgf_set_sm_reserve): a collective CTA that queues behind a persistent
+                 grid, or a GEMM cluster that queues behind a collective CTA, costs far more than the SMs given up.
+                 Measured at 2 GPUs (profiles/r2_fanout.txt): an upload takes 8.1 ms with 8 CTAs (6.1 ms of it the H2D),
+                 13.8 ms with 2; end to end 0.88 / 0.94 / 0.95 / 0.96 of the HBM-resident rate with 1 / 2 / 4 / 8 CTAs
+                 against 0.98 for plain per-GPU uploads -- the exchange only pays where the host link is the limit
+                 (8 GPUs: 0.88 without it).
+    mode='p2p'   the destination buffers of every rank are mapped into every process (CUDA IPC) and each rank PUSHES its
+                 rows into its peers' buffers with cudaMemcpyPeerAsync (pgf_memcpy_peer_async); two scalar all-reduces
+                 per upload order the pushes against the consumers on the other ranks (buffer free / rows landed).  On
+                 the virtualised boxes of this pool copies into another process's IPC mapping are staged through the
+                 host (measured 25 GB/s and 17 ms of blocked host time per upload), so it is not the default.
+    `register` falls back from 'p2p' to 'nccl' on every rank if any rank cannot map a peer buffer."""
+
+    def __init__(self, batch, device, mode="nccl", max_ctas=8, reserve_sms=None):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        if batch % self.world:
+            raise ValueError(f"the shared batch of {batch} rows does not split evenly over {self.world} ranks")
+        self.rows = batch // self.world
+        self.lo, self.hi = self.rank * self.rows, (self.rank + 1) * self.rows
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.mode = mode if (self.cuda and self.world > 1) else "nccl"
+        self.max_ctas = int(max_ctas) if self.mode == "nccl" else 1     # p2p: the communicator only carries the two scalar barriers
+        # SMs the GEMM grids leave free while this object is live: the collective's CTAs ('nccl'), or one CTA pair for the
+        # barrier kernels ('p2p' -- without it a barrier waits for a GEMM boundary on every rank, and while it spins for
+        # the slowest rank it holds an SM that the next GEMM's static tile schedule counts on: measured 0.91 instead of 0.97)
+        self.reserve_sms = (self.max_ctas if self.mode == "nccl" else 2) if reserve_sms is None else int(reserve_sms)
+        self.group = None
+        self.peers = {}          # slot -> list over ranks of the list of that rank's destination tensors (None for self)
+        self._flag = None
+        self._reserved = False
+
+    # ---- setup ----------------------------------------------------------------------------------
+    def _nccl_group(self):
+        if self.group is None and self.world > 1:
+            kw = {}
+            if self.cuda:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = self.max_ctas
+                opts.config.min_ctas = 1
+                kw = dict(backend="nccl", pg_options=opts)
+            self.group = dist.new_group(**kw)        # collective: every rank gets here together (see register)
+            if self.cuda and self.reserve_sms > 0:
+                from . import _lib
+                _lib.load().pgf_set_sm_reserve(self.reserve_sms)
+                self._reserved = True
+        return self.group
+
+    def register(self, slots):
+        """slots: {slot: [destination tensors of that slot, each [B, ...]]} -- the buffers `upload` will fill.  Called once
+        by every rank with the same structure.  In 'p2p' mode the buffers' CUDA IPC handles are exchanged and mapped."""
+        self.slots = {k: list(v) for k, v in slots.items()}
+        if self.world == 1:
+            return self.mode
+        if self.mode == "p2p":
+            try:
+                mine = {k: [(t.untyped_storage()._share_cuda_(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t.dtype)
+                            for t in v] for k, v in self.slots.items()}
+                ok = True
+            except Exception as e:          # noqa: BLE001 -- any failure means "use the other transport", on every rank
+                mine, ok = repr(e), False
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, (ok, mine))
+            ok = all(o for o, _ in everyone)
+            if ok:
+                try:
+                    for k in self.slots:
+                        per_rank = []
+                        for r, (_, handles) in enumerate(everyone):
+                            if r == self.rank:
+                                per_rank.append(None)
+                                continue
+                            ts = []
+                            for h, off, shape, stride, dtype in handles[k]:
+                                st = torch.UntypedStorage._new_shared_cuda(*h)
+                                ts.append(torch.empty(0, dtype=dtype, device=st.device).set_(st, off, shape, stride))
+                            per_rank.append(ts)
+                        self.peers[k] = per_rank
+                    self._flag = torch.zeros(1, device=self.device)
+                except Exception:           # noqa: BLE001
+                    ok = False
+            agreed = [None] * self.world
+            dist.all_gather_object(agreed, ok)
+            if not all(agreed):
+                self.peers, self.mode = {}, "nccl"
+        self._nccl_group()
+        return self.mode
+
+    def host_slice(self, t: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a host-side batch tensor."""
+        return t[self.lo:self.hi]
+
+    # ---- per step -------------------------------------------------------------------------------
+    def upload(self, slot, host_slices):
+        """host_slices[i] ([B/N, ...], pinned) -> rows [lo, hi) of the slot's i-th destination tensor on EVERY rank.
+        Enqueued on the current stream, which must already wait for this rank's consumers of the slot; returns once the
+        work is queued.  After it (in stream order) the slot holds the whole batch."""
+        dst = self.slots[slot]
+        if self.world == 1:
+            for hs, dt in zip(host_slices, dst):
+                dt.copy_(hs, non_blocking=True)
+            return
+        if self.mode == "nccl":
+            for hs, dt in zip(host_slices, dst):
+                mine = dt[self.lo:self.hi]
+                mine.copy_(hs, non_blocking=True)
+                dist.all_gather_into_tensor(dt, mine, group=self._nccl_group())
+            return
+        dist.all_reduce(self._flag, group=self.group)     # every rank's consumers have released the slot
+        for hs, dt in zip(host_slices, dst):
+            dt[self.lo:self.hi].copy_(hs, non_blocking=True)
+        from . import _lib
+        stream = torch.cuda.current_stream().cuda_stream
+        for r in range(1, self.world):                    # staggered so that the ranks do not all push to the same peer at once
+            q = (self.rank + r) % self.world
+            for dt, pt in zip(dst, self.peers[slot][q]):
+                src, to = dt[self.lo:self.hi], pt[self.lo:self.hi]
+                # raw cudaMemcpyPeerAsync on this rank's stream (a torch copy_ between devices of two processes is staged
+                # and blocks the host: measured 17 ms per upload)
+                _lib.call("pgf_memcpy_peer_async", to.data_ptr(), pt.device.index, src.data_ptr(), dt.device.index,
+                          src.numel() * src.element_size(), stream)
+        dist.all_reduce(self._flag, group=self.group)     # every rank's pushes have landed
+
+    def close(self):
+        if self._reserved:
+            from . import _lib
+            _lib.load().pgf_set_sm_reserve(0)
+            self._reserved = False
+        self.peers = {}
+
+
 def gather_metrics(local: dict, group=None):
     """Host-side gather of per-model metrics {model_index: value} from all ranks (epoch end)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

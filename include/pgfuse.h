@@ -242,6 +242,11 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
 int pgf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 /* zero-fill (the split-K weight-gradient GEMMs accumulate into a zeroed buffer; replaces grad.zero_()) */
 int pgf_fill_zero(void* p, size_t nbytes, void* stream);
+/* Device-to-device copy between two GPUs of the box on `stream` (a stream of the CURRENT device), executed by the copy
+ * engines over NVLink: cudaMemcpyPeerAsync with direct peer access enabled on first use.  dst / src may be mappings of
+ * another process's allocation (CUDA IPC).  Used to fan a shared sweep batch out to the peers' input buffers without SMs
+ * (replaces: one full DataLoader batch `.cuda()` per process, past_acc.py:192-196 run once per GPU). */
+int pgf_memcpy_peer_async(void* dst, int dst_device, const void* src, int src_device, size_t nbytes, void* stream);
 size_t pgf_colsum_workspace(int B, int N);
 int pgf_colsum(const void* x, int dtype, long long ld, int B, int N, float* out, float* workspace,
                size_t workspace_bytes, void* stream);

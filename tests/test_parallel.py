@@ -58,6 +58,15 @@ def _worker(rank, world, port, out_dir):
         ov.bucket(bucketed[a:b])
     ov.finish()
     assert ov.active and ov.n_buckets == 3 and torch.equal(bucketed, mine)
+    # shared sweep batch: every rank uploads its rows only, the exchange fills in the peers' rows
+    fan = parallel.SharedBatchFanout(GB, "cpu")
+    shared = torch.arange(GB * 3, dtype=torch.float32).view(GB, 3)
+    lab = torch.arange(GB)
+    dev_t, dev_l = torch.full((GB, 3), -1.0), torch.full((GB,), -1, dtype=torch.int64)
+    assert fan.register({0: [dev_t, dev_l]}) == "nccl"          # CPU / gloo: the collective transport
+    fan.upload(0, [fan.host_slice(shared), fan.host_slice(lab)])
+    assert (fan.lo, fan.hi) == parallel.batch_slice(GB, world, rank) and torch.equal(dev_t, shared) and torch.equal(dev_l, lab)
+    fan.close()
     # sweep mode: disjoint ownership, metrics gathered on every rank
     own = parallel.shard_models(5, world, rank)
     merged = parallel.gather_metrics({m: 0.9 + 0.01 * m for m in own})
