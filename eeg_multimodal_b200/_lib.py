@@ -100,6 +100,7 @@ def load() -> C.CDLL:
 
 
 # kernels launched per successful call (for the bench's `gpu_launches` count)
+WIDE_MODELS = 24     # PGF_WIDE_MODELS in csrc/pgf_kernels.cuh
 LAUNCHES_PER_CALL = {"pgf_memcpy_peer_async": 0, "pgf_perturb_gate_bwd_dp": 2, "pgf_gemm_bf16_ddp": 2, "pgf_cls_ce": 2, "pgf_colsum": 2, "pgf_prigumbel_bwd": 2}
 launch_count = 0
 launch_by_name = {}
@@ -112,6 +113,8 @@ def launches_of(name: str, args) -> int:
         return 1
     if name == "pgf_perturb_gate_bwd_dp" and args[4] <= 32:      # B <= 32: one slab, no finalize launch
         return 1
+    if name == "pgf_linear_bwd_dx" and args[12] <= 8 and args[15] >= WIDE_MODELS:   # slab kernel + finalize (linear_wide.cu)
+        return 2
     return LAUNCHES_PER_CALL.get(name, 1)
 
 

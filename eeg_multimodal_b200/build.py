@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgfuse.so")
-SOURCES = ["capi.cu", "perturb_gate.cu", "linear_simt.cu", "linear_stream.cu", "gemm_tc.cu", "fp32x3.cu", "ce_cls.cu", "adam.cu", "prigumbel.cu", "sweep_step.cu"]
+SOURCES = ["capi.cu", "perturb_gate.cu", "linear_simt.cu", "linear_stream.cu", "linear_wide.cu", "gemm_tc.cu", "fp32x3.cu", "ce_cls.cu", "adam.cu", "prigumbel.cu", "sweep_step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

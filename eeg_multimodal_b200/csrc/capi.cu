@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include "../../include/pgfuse.h"
+#include <stdlib.h>
+
 #include "pgf_kernels.cuh"
 
 namespace pgf {
@@ -214,9 +216,21 @@ int pgf_linear_fwd(const float* X, long long ldx, long long sX, const float* W, 
   return linear_fwd(a, n_models, static_cast<cudaStream_t>(stream));
 }
 
+// Few models per GPU at the reference batch: the TMA-ring kernels of linear_stream.cu (short launches, ramp-up and tail
+// matter).  Many models per launch: the slab kernels of linear_wide.cu (millisecond launches, page locality matters).
+// PGF_LINEAR_WIDE=0/1 forces one or the other.
+static bool wide_regime(int B, int n_models) {
+  static const char* env = getenv("PGF_LINEAR_WIDE");
+  if (env) return env[0] == '1';
+  return B <= 8 && n_models >= PGF_WIDE_MODELS;
+}
+
 size_t pgf_linear_bwd_dx_workspace(int B, int N, int K, int n_models) {
   if (B <= 0 || n_models <= 0) return 0;
-  return linear_dx_workspace(B, N, K, n_models);
+  const size_t ring = linear_dx_workspace(B, N, K, n_models);
+  if (!wide_regime(B, n_models)) return ring;
+  const size_t wide = linear_dx_workspace_wide(B, N, K, n_models);
+  return wide > ring ? wide : ring;
 }
 
 int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float* W, long long sW, const float* mask_src,
@@ -227,6 +241,9 @@ int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float
   PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(W) && aligned16(dX) && (sW % 4) == 0 && (sdX % 4) == 0 &&
                     (!mask_src || ((ld_mask % 4) == 0 && aligned16(mask_src) && (s_mask % 4) == 0)),
                 "pgf_linear_bwd_dx: K, ldx, strides must be multiples of 4 and W, dX, mask 16-byte aligned");
+  if (wide_regime(B, n_models))
+    return linear_bwd_dx_wide(dY, ldy, sdY, W, sW, mask_src, mask_mode, ld_mask, s_mask, dX, ldx, sdX, B, N, K, n_models, workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
   return linear_bwd_dx(dY, ldy, sdY, W, sW, mask_src, mask_mode, ld_mask, s_mask, dX, ldx, sdX, B, N, K, n_models, workspace,
                        workspace_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -389,6 +406,7 @@ int pgf_linear_adam_step(const float* dY, long long ldy, long long sdY, const fl
   l.bias = bias; l.mb = mb; l.vb = vb; l.N = N; l.K = K;
   a.n_layers = 1; a.sP = sP; a.B = B; a.st = nullptr; a.adv = StepAdvance{};
   a.c = make_adam_coef(step, lr, beta1, beta2, eps, grad_scale);
+  if (wide_regime(B, n_models)) return linear_adam_step_wide(a, n_models, static_cast<cudaStream_t>(stream));
   return linear_adam_step(a, n_models, static_cast<cudaStream_t>(stream));
 }
 

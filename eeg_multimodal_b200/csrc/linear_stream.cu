@@ -810,7 +810,9 @@ int linear_adam_step(const LinAdamArgs& in, int n_models, cudaStream_t s) {
     row_blocks[i] = (l.N + LS_ROWS - 1) / LS_ROWS;
   }
   // one item height for every layer, so that contiguous item ranges are equal amounts of work
-  const int bp = ls_pick_blocks(units, row_blocks, in.n_layers, num_sms(), 36, 1, 0);
+  static const int bp_env = getenv("PGF_LS_ADAM_BP") ? atoi(getenv("PGF_LS_ADAM_BP")) : 0;
+  int bp = ls_pick_blocks(units, row_blocks, in.n_layers, num_sms(), 36, 1, 0);
+  if (bp_env > 0) bp = bp_env;
   int n_items = 0, rows_max = 0;
   for (int i = 0; i < in.n_layers; ++i) {
     const LinAdamLayer& l = in.l[i];

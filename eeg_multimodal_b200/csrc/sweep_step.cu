@@ -61,6 +61,11 @@ struct SweepPlan {
     size_t dxp = linear_dx_workspace(B, H, D, M);
     const size_t dxp1 = linear_dx_workspace(B, D, D, M);
     if (dxp1 > dxp) dxp = dxp1;
+    if (M >= PGF_WIDE_MODELS) {   // many models per GPU: the slab kernels of linear_wide.cu take dX and gradient+Adam
+      const size_t w0 = linear_dx_workspace_wide(B, H, D, M), w1 = linear_dx_workspace_wide(B, D, D, M);
+      if (w0 > dxp) dxp = w0;
+      if (w1 > dxp) dxp = w1;
+    }
     dxp = align256(dxp);
     const size_t ce = align256(cls_ce_workspace(B, H, M));
     const size_t cnt = align256((static_cast<size_t>(linear_dx_counters(B, D, M)) + 1) * sizeof(unsigned int));   // + the step-advance ticket
@@ -142,13 +147,18 @@ int SweepPlan::pass(cudaStream_t s, bool model_pass, bool first_pdl, unsigned in
     if (rc != PGF_OK) return rc;
   }
   // (a11) dZ1 = (dZ2 . W2) * relu'(H1)
-  rc = linear_bwd_dx(dZ2, H, static_cast<long long>(B) * H, W2, d.P, H1, PGF_ACT_RELU, D, static_cast<long long>(B) * D, dZ1, D,
-                     static_cast<long long>(B) * D, B, H, D, M, dx_part, dx_part_bytes, s, counters);
+  const bool wide = M >= PGF_WIDE_MODELS;   // millisecond launches: page locality decides, not ramp-up and tail (linear_wide.cu)
+  rc = wide ? linear_bwd_dx_wide(dZ2, H, static_cast<long long>(B) * H, W2, d.P, H1, PGF_ACT_RELU, D, static_cast<long long>(B) * D,
+                                 dZ1, D, static_cast<long long>(B) * D, B, H, D, M, dx_part, dx_part_bytes, s)
+            : linear_bwd_dx(dZ2, H, static_cast<long long>(B) * H, W2, d.P, H1, PGF_ACT_RELU, D, static_cast<long long>(B) * D, dZ1, D,
+                            static_cast<long long>(B) * D, B, H, D, M, dx_part, dx_part_bytes, s, counters);
   if (rc != PGF_OK) return rc;
   if (!model_pass) {
     // dX = dZ1 . W1, then dDP + Adam(DP) + coefficient refresh
-    rc = linear_bwd_dx(dZ1, D, static_cast<long long>(B) * D, W1, d.P, nullptr, PGF_ACT_RELU, 0, 0, dX, D,
-                       static_cast<long long>(B) * D, B, D, D, M, dx_part, dx_part_bytes, s, counters);
+    rc = wide ? linear_bwd_dx_wide(dZ1, D, static_cast<long long>(B) * D, W1, d.P, nullptr, PGF_ACT_RELU, 0, 0, dX, D,
+                                   static_cast<long long>(B) * D, B, D, D, M, dx_part, dx_part_bytes, s)
+              : linear_bwd_dx(dZ1, D, static_cast<long long>(B) * D, W1, d.P, nullptr, PGF_ACT_RELU, 0, 0, dX, D,
+                              static_cast<long long>(B) * D, B, D, D, M, dx_part, dx_part_bytes, s, counters);
     if (rc != PGF_OK) return rc;
     DpAdamFuse f;
     f.DP = d.DP; f.DP_m = d.DP_m; f.DP_v = d.DP_v;
@@ -176,7 +186,7 @@ int SweepPlan::pass(cudaStream_t s, bool model_pass, bool first_pdl, unsigned in
   a.adv.counter = counters + linear_dx_counters(B, D, M);
   a.adv.d_noise = d.dp_pass ? 2 : 1; a.adv.d_tdp = d.dp_pass ? 1 : 0; a.adv.d_tmodel = 1;
   a.adv.d_cursor = B; a.adv.n_rows = d.n_rows;
-  return linear_adam_step(a, M, s);
+  return wide ? linear_adam_step_wide(a, M, s) : linear_adam_step(a, M, s);
 }
 
 int SweepPlan::enqueue(cudaStream_t s, bool first_pdl) {
@@ -324,7 +334,10 @@ int pgf_sweep_plan_run(void* plan, void* stream, int n_steps) {
 
 int pgf_sweep_plan_launches_per_step(void* plan) {
   if (!plan) return 0;
-  return static_cast<SweepPlan*>(plan)->d.dp_pass ? 13 : 6;
+  const SweepPlan* p = static_cast<const SweepPlan*>(plan);
+  if (p->d.n_models >= PGF_WIDE_MODELS)   // slab kernels: dX = kernel + finalize, gradient+Adam = one launch per layer + the state advance
+    return p->d.dp_pass ? 18 : 9;
+  return p->d.dp_pass ? 13 : 6;
 }
 
 int pgf_sweep_plan_destroy(void* plan) {

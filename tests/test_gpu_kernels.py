@@ -304,7 +304,7 @@ def test_adam_matches_torch(dev):
     assert torch.equal(shadow, pd.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("n_models,B,N,K", [(2, 8, 96, 256), (3, 5, 64, 192), (1, 8, 768, 2304)])
+@pytest.mark.parametrize("n_models,B,N,K", [(2, 8, 96, 256), (3, 5, 64, 192), (1, 8, 768, 2304), (24, 8, 96, 256), (30, 3, 64, 192)])
 def test_linear_adam_streaming_kernel_is_bit_identical_to_dw_plus_adam(dev, n_models, B, N, K):
     """The TMA-fed gradient+Adam kernel (straight-line IEEE division / square-root sequences, library fallback per warp)
     against linear_bwd_dw + adam_step (library __fdiv_rn / __fsqrt_rn), bit for bit, with moments and gradients spread

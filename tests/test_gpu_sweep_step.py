@@ -19,7 +19,7 @@ def dev():
 def _engines(dev, M, dims, H, lr=1e-3, eps=None, seeds=None, dp_init=None):
     from eeg_multimodal_b200 import HeadEngine
 
-    eps = eps or [0.1, 1.0, 3.0, 8.0][:M]
+    eps = eps or [[0.1, 1.0, 3.0, 8.0][i % 4] for i in range(M)]
     seeds = seeds or [980616 + 7 * i for i in range(M)]        # not an arithmetic progression of step 1
     kw = dict(n_models=M, feature_dims=dims, hidden=H, eps=eps, seeds=seeds, lr=lr, precision="fp32", init_seed=11, dp_init=dp_init)
     return HeadEngine(**kw), HeadEngine(**kw)
@@ -43,7 +43,8 @@ def _dataset(dev, n, dims, seed=3):
 
 
 @pytest.mark.parametrize("use_pdl", [False, True])
-@pytest.mark.parametrize("dims,H,M,B", [((768, 768, 768), 768, 3, 8), ((128, 64), 32, 4, 8), ((256, 128, 128), 64, 2, 3)])
+@pytest.mark.parametrize("dims,H,M,B", [((768, 768, 768), 768, 3, 8), ((128, 64), 32, 4, 8), ((256, 128, 128), 64, 2, 3),
+                                        ((128, 64), 32, 24, 8), ((256, 128, 128), 64, 26, 5)])   # >= 24 models: the slab kernels of linear_wide.cu
 def test_plan_is_bit_identical_to_the_engine_path(dev, dims, H, M, B, use_pdl):
     from eeg_multimodal_b200.sweep_plan import SweepStepPlan
 
