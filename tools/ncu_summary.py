@@ -37,6 +37,11 @@ BENCH_NAMES = {
     "r1_gemm_dW2": ("gemm_bf16_tc M=768 N=2560 K=65536 a_mn=1 b_mn=1 epi=4", 1),
     "r1_cls_ce_pass2": ("cls_ce B=65536 H=768 models=6 bwd=2", 6),
     "r1_cls_ce_pass1": ("cls_ce B=65536 H=768 models=6 bwd=1", 6),
+    "r2_gemm_x3_fwd1": ("gemm_bf16x3_tc M=65536 N=2560 K=2560 a_mn=0 b_mn=0 epi=4", 1),
+    "r2_gemm_x3_dW1": ("gemm_bf16x3_tc M=2560 N=2560 K=65536 a_mn=1 b_mn=1 epi=4", 1),
+    "r2_split3": ("split3 R=65536 C=2560 act=1 planes=1 out=0 mask=0", 1),
+    "r2_wide_adam_W1": ("linear_adam B=8 N=2304 K=2304 models=128", 1),
+    "r2_wide_dx_W1": ("linear_bwd_dx B=8 N=2304 K=2304 models=128", 1),
 }
 
 

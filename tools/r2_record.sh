@@ -22,3 +22,14 @@ except Exception as e:
     print(sys.argv[1], 'FAILED', e); print(open(sys.argv[1]).read()[-800:])
 PY
 done
+# single-GPU view of one data-parallel rank at 8 GPUs (8,192 rows per GPU, no exchange): where its step time goes
+timeout 300 python bench.py --workload dp64k --batch 8192 --no-cpu-baseline --no-e2e --steps 100 > $O/r2_bench_dp64k_rank_of_8.json 2> $O/dp8192.err
+# ncu --set full captures of the round-2 kernels
+mkdir -p /tmp/rep $O/prof; cp profiles/ncu_traffic.json $O/prof/ 2>/dev/null
+cap() { stem=$1; regex=$2; shift; shift; timeout 240 ncu --set full --clock-control none --import-source on --launch-skip 2 --launch-count 1 -k regex:"$regex" -o /tmp/rep/$stem -f python tools/ncu_targets.py "$@" > $O/ncu_$stem.log 2>&1; }
+cap r2_gemm_x3_fwd1 gemm_bf16_tc x3_fwd1
+cap r2_gemm_x3_dW1 gemm_bf16_tc x3_dW1
+cap r2_split3 split3_kernel split3
+cap r2_wide_adam_W1 wide_adam_kernel wide_adam_W1
+cap r2_wide_dx_W1 wide_dx_kernel wide_dx_W1
+python tools/ncu_summary.py --outdir=$O/prof /tmp/rep/r2_*.ncu-rep > $O/ncu_summary.log 2>&1; tail -6 $O/ncu_summary.log
