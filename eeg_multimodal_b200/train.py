@@ -63,7 +63,9 @@ def build_parser():
     p.add_argument("--variants", type=str, default=None,
                    help="comma list of DP initialisation variants (zeros,newinit,tt,newinit_k1,newinit_k3,feawei): model_dict/newfrac_*")
     p.add_argument("--lr", type=float, default=1e-6)        # past_acc.py:157, train.py:75
-    p.add_argument("--precision", choices=["fp32", "bf16"], default="fp32")
+    p.add_argument("--precision", choices=["fp32", "bf16", "fp32x3"], default="fp32",
+                   help="arithmetic of the dense layers: fp32 = the reference's (CUDA-core kernels at the reference batch sizes, the "
+                        "fp32x3 tensor-core route from 1,024 rows on), fp32x3 = always that route, bf16 = bf16 GEMM operands")
     p.add_argument("--unfixed-formula", action="store_true", help="eps_hat = log(..) as in model.py:57 (new_*eps runs)")
     p.add_argument("--records-root", type=str, default=None, help="also write model_dict-style records per model")
     return p
