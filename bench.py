@@ -218,7 +218,9 @@ def kernel_table(timing, total_ms, steps, peaks, peak_kind):
             peak, unit, pk = peaks["hbm_gbs"], "GB/s", "copy bandwidth"
             achieved = work / (t_ms / n * 1e-3) / 1e9
         rows.append({"kernel": name, "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": unit,
-                     "frac": round(achieved / peak, 4), "peak_kind": f"{peak_kind} ({pk})", "traffic": traffic.get(name),
+                     "frac": round(achieved / peak, 4), "peak_kind": f"{peak_kind} ({pk})",
+                     **({"frac_vs_8tbs_nominal": round(achieved / 8000.0, 4)} if bound == "hbm" else {}),   # north_star quotes ~8 TB/s
+                     "traffic": traffic.get(name),
                      "share_of_step": round(t_ms / total_ms, 4), "avg_launch_ms": round(t_ms / n, 4), "launches_per_step": n / steps})
     timed = sum(v[0] for v in agg.values())
     top = dict(rows[0])
