@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpgfuse.so")
 DT_F32, DT_BF16 = 0, 1
 NOISE_INJECTED, NOISE_PHILOX, NOISE_NONE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, EPI_RELUMASK_BF16, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32, EPI_BIAS_TANH_F32, EPI_DDP_PARTIAL, EPI_BITMASK_BF16 = range(10)
+EPI_STORE_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_TANH_BF16, _EPI_RETIRED_3, EPI_ATOMIC_F32, EPI_STORE_F32, EPI_BIAS_F32, EPI_BIAS_TANH_F32, EPI_DDP_PARTIAL, EPI_BITMASK_BF16 = range(10)
 
 P, I, LL, F, U32, U64, SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_uint, C.c_ulonglong, C.c_size_t
 

@@ -275,7 +275,7 @@ int pgf_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
                   int M, int N, int K, int epi, const float* bias, void* aux, long long ld_aux, int stream_k,
                   float* col_partial, void* stream) {
   PGF_CHECK_ARG(A && B && C, "pgf_gemm_bf16: NULL operand");
-  PGF_CHECK_ARG((epi >= 0 && epi <= 7) || epi == 9, "pgf_gemm_bf16: bad epilogue %d", epi);
+  PGF_CHECK_ARG((epi >= 0 && epi <= 7 && epi != 3) || epi == 9, "pgf_gemm_bf16: bad epilogue %d", epi);
   if (epi == PGF_EPI_BIAS_RELU_BF16 || epi == PGF_EPI_BIAS_TANH_BF16 || epi == PGF_EPI_BIAS_F32 || epi == PGF_EPI_BIAS_TANH_F32)
     PGF_CHECK_ARG(bias && aligned16(bias), "pgf_gemm_bf16: epilogue needs a 16-byte aligned bias");
   GemmArgs g = {};

@@ -37,7 +37,6 @@ namespace pgf {
 #define PGF_EPI_STORE_BF16 0        // C = acc
 #define PGF_EPI_BIAS_RELU_BF16 1    // C = relu(acc + bias[n])
 #define PGF_EPI_BIAS_TANH_BF16 2    // C = tanh(acc + bias[n])
-#define PGF_EPI_RELUMASK_BF16 3     // retired (bf16 mask-source tile); use PGF_EPI_BITMASK_BF16
 #define PGF_EPI_ATOMIC_F32 4        // C(fp32) += acc                    (stream-K partials)
 #define PGF_EPI_STORE_F32 5         // C(fp32) = acc
 #define PGF_EPI_BIAS_F32 6          // C(fp32) = acc + bias[n]
@@ -693,10 +692,6 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
               cudaStream_t s) {
   GemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PGF_OK;
-  if (g.epi == PGF_EPI_RELUMASK_BF16) {
-    set_error("pgf_gemm_bf16: the bf16 mask-source epilogue (3) was retired; write the ReLU sign bits with epilogue 1 and apply them with epilogue 9");
-    return PGF_ERR_UNSUPPORTED;
-  }
   const bool out_f32 = g.epi == PGF_EPI_ATOMIC_F32 || g.epi == PGF_EPI_STORE_F32 || g.epi == PGF_EPI_BIAS_F32 ||
                        g.epi == PGF_EPI_BIAS_TANH_F32;
   if ((g.N % 8) || (lda % 8) || (ldb % 8) || (g.epi != PGF_EPI_DDP_PARTIAL && (g.ldc % (out_f32 ? 4 : 8))) ||

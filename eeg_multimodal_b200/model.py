@@ -282,13 +282,15 @@ class ConcatModel(nn.Module):
 
 def get_model(cfg):
     """reference model.py:8-12.  `cfg.data_name == 'EEG'` builds ConcatModel; `cfg.eps` is the
-    privacy budget.  Optional extras: cfg.feature_dims, cfg.private, cfg.fixed_formula."""
+    privacy budget.  Optional extras: cfg.feature_dims, cfg.private, cfg.fixed_formula, cfg.precision, cfg.tc_min_batch."""
     if not torch.cuda.is_available():
         raise RuntimeError("get_model needs a CUDA device (the reference calls .cuda() too, model.py:11-12)")
     if cfg.data_name == 'EEG':
         model = ConcatModel(feature_dims=getattr(cfg, "feature_dims", (768, 768, 768)),
                             private=getattr(cfg, "private", True),
-                            fixed_formula=getattr(cfg, "fixed_formula", True))
+                            fixed_formula=getattr(cfg, "fixed_formula", True),
+                            precision=getattr(cfg, "precision", "fp32"),
+                            tc_min_batch=getattr(cfg, "tc_min_batch", 1024))
     else:
         raise ValueError(f"unknown data_name {cfg.data_name!r} (the reference only defines 'EEG')")
     model.eps = torch.tensor(cfg.eps).cuda()

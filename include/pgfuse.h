@@ -40,7 +40,7 @@ extern "C" {
 #define PGF_EPI_STORE_BF16 0
 #define PGF_EPI_BIAS_RELU_BF16 1
 #define PGF_EPI_BIAS_TANH_BF16 2
-#define PGF_EPI_RELUMASK_BF16 3 /* retired: returns PGF_ERR_UNSUPPORTED (superseded by the sign-bit mask, 9) */
+/* 3 is not an epilogue any more (a bf16 mask-source tile, superseded by the sign-bit mask 9): rejected as a bad argument */
 #define PGF_EPI_ATOMIC_F32 4
 #define PGF_EPI_STORE_F32 5
 #define PGF_EPI_BIAS_F32 6

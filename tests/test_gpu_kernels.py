@@ -400,8 +400,8 @@ def test_gemm_bf16_epilogues(dev):
     for epi, ref in ((L.EPI_STORE_BF16, z), (L.EPI_BIAS_RELU_BF16, torch.relu(zb)), (L.EPI_BIAS_TANH_BF16, torch.tanh(zb))):
         ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=epi, bias=bias)
         assert rel_err(out, ref) < 6e-3, (epi, rel_err(out, ref))   # bf16 output rounding: 2^-8
-    with pytest.raises(RuntimeError):                              # the bf16 mask-source epilogue was retired
-        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=L.EPI_RELUMASK_BF16)
+    with pytest.raises(RuntimeError):                              # 3 (a bf16 mask-source tile) is no epilogue any more
+        ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=3)
     # ReLU sign bits: written by the forward epilogue (one uint32 per row x 32 columns), applied by the backward one
     bits = torch.full((M, N // 32), -1, dtype=torch.int32, device=dev)
     ops.gemm_bf16(A, W, out, M=M, N=N, K=K, epi=L.EPI_BIAS_RELU_BF16, bias=bias, aux=bits)
