@@ -518,6 +518,7 @@ class HeadEngine:
                 self.t_dp += d[1]
                 self.t_model += d[2]
                 self._coef_key = self._coef_state()      # the replayed pass 2 recomputed the rows after the DP update
+                self._planes_key = None                  # the replayed Adam moved the weights after the step's own split
                 return self._result(ent["stats"])
             self._plans.pop(key)          # the step state no longer advances the way it did while recording
             ent = None
