@@ -274,3 +274,53 @@ def test_launch_accounting_follows_the_single_launch_paths():
         ce[10], bw[4] = B, B
         assert _lib.launches_of("pgf_cls_ce", ce) == n_ce and _lib.launches_of("pgf_perturb_gate_bwd_dp", bw) == n_bw
     assert _lib.launches_of("pgf_gemm_bf16_ddp", ()) == 2 and _lib.launches_of("pgf_adam_step", ()) == 1
+
+
+def test_launch_accounting_of_the_many_models_regime():
+    """From 24 models per launch on, pgf_linear_bwd_dx is the slab kernel + its finalize launch (csrc/linear_wide.cu)."""
+    from eeg_multimodal_b200 import _lib
+
+    args = [0] * 19
+    args[12] = 8
+    for n_models, want in ((6, 1), (23, 1), (24, 2), (128, 2)):
+        args[15] = n_models
+        assert _lib.launches_of("pgf_linear_bwd_dx", args) == want
+    args[12], args[15] = 601, 48                       # larger batches stay on the ring kernel
+    assert _lib.launches_of("pgf_linear_bwd_dx", args) == 1
+    assert _lib.launches_of("pgf_memcpy_peer_async", ()) == 0     # a copy-engine transfer, not a kernel
+
+
+def test_bench_work_model_of_the_round2_kernels():
+    """bench.py's algorithmic work per launch for the fp32-parity kernels: six plane-pair products per fp32 multiply-add,
+    and split3's bytes (4 read + 6 per plane triple + 4 if the fp32 tensor is written too + 2 for the mask plane)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    name, bound, work = bench.kernel_work(("gemm_x3", 65536, 2560, 2560, 0, 0, 4))
+    assert bound == "tensor" and work == 12.0 * 65536 * 2560 * 2560 and "bf16x3" in name
+    _, bound, nbytes = bench.kernel_work(("split3", 65536, 2560, 1, 1, 0, 0))
+    assert bound == "hbm" and nbytes == 65536 * 2560 * 10
+    _, _, nbytes = bench.kernel_work(("split3", 65536, 2560, 0, 1, 1, 1))
+    assert nbytes == 65536 * 2560 * 16
+    # one reference step skips the gradients the reference discards: 8 D^2 + 10 D H per sample
+    assert bench.flops_per_sample_step(2560, 768) == 8 * 2560 * 2560 + 10 * 2560 * 768
+
+
+def test_single_process_fanout_and_inactive_overlap_hook():
+    """World size 1: the shared-batch upload is a plain copy and the bucketed exchange hook only counts its buckets."""
+    from eeg_multimodal_b200 import parallel
+
+    fan = parallel.SharedBatchFanout(6, "cpu")
+    dst = [torch.zeros(6, 3), torch.zeros(6, dtype=torch.int64)]
+    assert fan.register({0: dst}) == "nccl" and (fan.lo, fan.hi) == (0, 6)
+    src = [torch.arange(18.0).view(6, 3), torch.arange(6)]
+    fan.upload(0, [fan.host_slice(t) for t in src])
+    assert torch.equal(dst[0], src[0]) and torch.equal(dst[1], src[1])
+    fan.close()
+    hook = parallel.OverlappedAllReduce(w1_chunks=5)
+    g = torch.ones(10)
+    hook.bucket(g[:4]); hook.bucket(g[4:]); hook.finish(); hook(g)
+    assert not hook.active and hook.n_buckets == 2 and torch.equal(g, torch.ones(10))
