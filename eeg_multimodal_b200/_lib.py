@@ -33,6 +33,8 @@ SIGNATURES = {
     "pgf_linear_bwd_dx_workspace": (SZ, [I, I, I, I]),
     "pgf_linear_bwd_dx": (I, [P, LL, LL, P, LL, P, I, LL, LL, P, LL, LL, I, I, I, I, P, SZ, P]),
     "pgf_linear_bwd_dw": (I, [P, LL, LL, P, LL, LL, P, LL, P, LL, I, I, I, I, I, P]),
+    "pgf_linear_bwd_dw_workspace": (SZ, [I, I, I, I]),
+    "pgf_linear_bwd_dw_ex": (I, [P, LL, LL, P, LL, LL, P, LL, P, LL, I, I, I, I, I, P, SZ, P]),
     "pgf_gemm_bf16": (I, [P, LL, I, P, LL, I, P, LL, I, I, I, I, P, P, LL, I, P, P]),
     "pgf_split3": (I, [P, LL, I, I, P, I, P, LL, P, LL, P, LL, LL, P]),
     "pgf_gemm_bf16x3": (I, [P, LL, LL, I, P, LL, LL, I, P, LL, I, I, I, I, P, I, P]),
@@ -113,6 +115,9 @@ def launches_of(name: str, args) -> int:
         return 1
     if name == "pgf_perturb_gate_bwd_dp" and args[4] <= 32:      # B <= 32: one slab, no finalize launch
         return 1
+    if name == "pgf_linear_bwd_dw_ex":   # narrow layer at a large batch: slab kernel + the reductions of dW (and db) per model
+        B, N, n_models, has_db = args[10], args[11], args[14], args[8] is not None
+        return 1 + n_models * (2 if has_db else 1) if (N <= 8 and B >= 512 and args[16] > 0) else 1
     if name == "pgf_linear_bwd_dx" and args[12] <= 8 and args[15] >= WIDE_MODELS:   # slab kernel + finalize (linear_wide.cu)
         return 2
     return LAUNCHES_PER_CALL.get(name, 1)

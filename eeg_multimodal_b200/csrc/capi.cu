@@ -248,6 +248,26 @@ int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float
                        workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+size_t pgf_linear_bwd_dw_workspace(int B, int N, int K, int n_models) {
+  if (B <= 0 || N <= 0 || K <= 0 || n_models <= 0) return 0;
+  return linear_dw_batch_workspace(B, N, K, n_models);
+}
+
+int pgf_linear_bwd_dw_ex(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX, float* dW,
+                         long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate, int n_models,
+                         float* workspace, size_t workspace_bytes, void* stream) {
+  if (n_models > 0 && B > 0 && workspace && linear_dw_batch_applies(B, N) && workspace_bytes >= linear_dw_batch_workspace(B, N, K, n_models)) {
+    PGF_CHECK_ARG(dY && X && dW && N > 0 && K > 0, "pgf_linear_bwd_dw_ex: NULL or non-positive argument");
+    PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(X) && aligned16(dW) && (sX % 4) == 0 && (sdW % 4) == 0 && aligned16(workspace),
+                  "pgf_linear_bwd_dw_ex: K, ldx, strides must be multiples of 4 and X, dW, workspace 16-byte aligned");
+    LinDwArgs a;
+    a.dY = dY; a.ldy = ldy; a.sdY = sdY; a.X = X; a.ldx = ldx; a.sX = sX; a.dW = dW; a.sdW = sdW; a.db = db; a.sdb = sdb;
+    a.B = B; a.N = N; a.K = K; a.rows_per_cta = 0; a.accumulate = accumulate;
+    return linear_bwd_dw_batch(a, n_models, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  }
+  return pgf_linear_bwd_dw(dY, ldy, sdY, X, ldx, sX, dW, sdW, db, sdb, B, N, K, accumulate, n_models, stream);
+}
+
 int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX, float* dW,
                       long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate, int n_models,
                       void* stream) {

@@ -94,4 +94,130 @@ int linear_bwd_dw(const LinDwArgs& a_in, int n_models, cudaStream_t s) {
   return PGF_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// dW, db of a NARROW layer at a LARGE batch (the 768 -> 2 classifier behind the module API, models.py:81, when
+// ConcatModel.forward runs on a 65,536-row batch): dW[n,k] = sum_b dY[b,n] X[b,k] with N <= 8.  linear_dw_kernel walks the
+// batch sequentially inside each CTA, and a 2-row layer gives it two CTAs (10 ms at B = 65,536); here the batch is cut into
+// slabs, one CTA per (column block, slab) keeps its N partial rows in registers, and the slab partials are summed in slab
+// order by reduce_partials (fixed order, no atomics).
+// ------------------------------------------------------------------------------------------
+struct LinDwBatchArgs {
+  const float* dY; long long ldy, sdY;
+  const float* X; long long ldx, sX;
+  float* partial;      // [n_models][nslab][N][K]
+  float* partial_db;   // [n_models][nslab][N]
+  int B, N, K, rows_per_slab, nslab;
+};
+
+template <int NN>
+__global__ void __launch_bounds__(128) linear_dw_batch_kernel(const LinDwBatchArgs a) {
+  extern __shared__ float sdy[];  // [rows of the slab][N]
+  const int model = blockIdx.z, slab = blockIdx.y;
+  const int b0 = slab * a.rows_per_slab, b1 = min(a.B, b0 + a.rows_per_slab), rows = b1 - b0;
+  const float* dY = a.dY + model * a.sdY;
+  for (int i = threadIdx.x; i < rows * a.N; i += blockDim.x) {
+    const int r = i / a.N, n = i - r * a.N;
+    sdy[i] = dY[static_cast<long long>(b0 + r) * a.ldy + n];
+  }
+  __syncthreads();
+  const long long unit = static_cast<long long>(model) * a.nslab + slab;
+  if (blockIdx.x == 0 && a.partial_db && threadIdx.x < a.N) {
+    float sum = 0.f;
+    for (int r = 0; r < rows; ++r) sum += sdy[r * a.N + threadIdx.x];
+    a.partial_db[unit * a.N + threadIdx.x] = sum;
+  }
+  const int k4 = blockIdx.x * blockDim.x + threadIdx.x, K4 = a.K >> 2;
+  if (k4 >= K4) return;
+  float4 acc[NN];
+#pragma unroll
+  for (int n = 0; n < NN; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* X = reinterpret_cast<const float4*>(a.X + model * a.sX + static_cast<long long>(b0) * a.ldx) + k4;
+  const long long ldx4 = a.ldx >> 2;
+  constexpr int U = 4;  // rows in flight per thread
+  int r = 0;
+  for (; r + U <= rows; r += U) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = ldg_stream(X + static_cast<long long>(r + u) * ldx4);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        if (n < a.N) {
+          const float g = sdy[(r + u) * a.N + n];
+          acc[n].x = fmaf(g, x[u].x, acc[n].x);
+          acc[n].y = fmaf(g, x[u].y, acc[n].y);
+          acc[n].z = fmaf(g, x[u].z, acc[n].z);
+          acc[n].w = fmaf(g, x[u].w, acc[n].w);
+        }
+      }
+    }
+  }
+  for (; r < rows; ++r) {
+    const float4 x = ldg_stream(X + static_cast<long long>(r) * ldx4);
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+      if (n < a.N) {
+        const float g = sdy[r * a.N + n];
+        acc[n].x = fmaf(g, x.x, acc[n].x);
+        acc[n].y = fmaf(g, x.y, acc[n].y);
+        acc[n].z = fmaf(g, x.z, acc[n].z);
+        acc[n].w = fmaf(g, x.w, acc[n].w);
+      }
+    }
+  }
+  float4* P = reinterpret_cast<float4*>(a.partial + unit * a.N * a.K) + k4;
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+    if (n < a.N) P[static_cast<long long>(n) * K4] = acc[n];
+}
+
+bool linear_dw_batch_applies(int B, int N) { return N <= 8 && B >= 512; }
+
+static int linear_dw_batch_slabs(int B, int K, int n_models) {
+  const int kctas = (K / 4 + 127) / 128;
+  long long slabs = (4LL * num_sms() + static_cast<long long>(kctas) * n_models - 1) / (static_cast<long long>(kctas) * n_models);
+  const long long max_slabs = (B + 63) / 64, min_slabs = (B + 1023) / 1024;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < min_slabs) slabs = min_slabs;
+  if (slabs < 1) slabs = 1;
+  return static_cast<int>(slabs);
+}
+
+size_t linear_dw_batch_workspace(int B, int N, int K, int n_models) {
+  if (!linear_dw_batch_applies(B, N)) return 0;
+  const size_t slabs = static_cast<size_t>(linear_dw_batch_slabs(B, K, n_models));
+  return static_cast<size_t>(n_models) * slabs * N * (static_cast<size_t>(K) + 1) * sizeof(float);
+}
+
+int linear_bwd_dw_batch(const LinDwArgs& in, int n_models, float* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (workspace_bytes < linear_dw_batch_workspace(in.B, in.N, in.K, n_models)) {
+    set_error("pgf_linear_bwd_dw_ex: workspace too small");
+    return PGF_ERR_WORKSPACE;
+  }
+  LinDwBatchArgs a;
+  a.dY = in.dY; a.ldy = in.ldy; a.sdY = in.sdY; a.X = in.X; a.ldx = in.ldx; a.sX = in.sX;
+  a.B = in.B; a.N = in.N; a.K = in.K;
+  a.nslab = linear_dw_batch_slabs(in.B, in.K, n_models);
+  a.rows_per_slab = (in.B + a.nslab - 1) / a.nslab;
+  a.nslab = (in.B + a.rows_per_slab - 1) / a.rows_per_slab;
+  a.partial = workspace;
+  a.partial_db = in.db ? workspace + static_cast<size_t>(n_models) * a.nslab * in.N * in.K : nullptr;
+  const dim3 grid((in.K / 4 + 127) / 128, a.nslab, n_models);
+  const size_t smem = static_cast<size_t>(a.rows_per_slab) * in.N * sizeof(float);
+  if (in.N <= 2) linear_dw_batch_kernel<2><<<grid, 128, smem, s>>>(a);
+  else if (in.N <= 4) linear_dw_batch_kernel<4><<<grid, 128, smem, s>>>(a);
+  else linear_dw_batch_kernel<8><<<grid, 128, smem, s>>>(a);
+  PGF_CUDA_LAUNCH_CHECK("pgf_linear_bwd_dw_ex");
+  for (int m = 0; m < n_models; ++m) {
+    int rc = reduce_partials(a.partial + static_cast<size_t>(m) * a.nslab * in.N * in.K, a.nslab, in.N * in.K, nullptr,
+                             in.dW + m * in.sdW, in.accumulate, s);
+    if (rc == PGF_OK && in.db)
+      rc = reduce_partials(a.partial_db + static_cast<size_t>(m) * a.nslab * in.N, a.nslab, in.N, nullptr, in.db + m * in.sdb,
+                           in.accumulate, s);
+    if (rc != PGF_OK) return rc;
+  }
+  return PGF_OK;
+}
+
 }  // namespace pgf

@@ -378,8 +378,10 @@ def linear_bwd_dw(dY, X, dW=None, db=None, want_db=True, accumulate=False):
         db = torch.empty((*lead, N), dtype=torch.float32, device=dY.device)
     sdW = dW.stride(0) if dW.dim() == 3 else 0
     sdb = 0 if db is None or db.dim() == 1 else db.stride(0)
-    _call(("linear_bwd_dw", B, N, K, n_models), "pgf_linear_bwd_dw", dY.data_ptr(), dY.stride(-2), sdY, X.data_ptr(), X.stride(-2), sX, dW.data_ptr(), sdW,
-           _ptr(db), sdb, B, N, K, int(accumulate), n_models, _stream())
+    nbytes = _query("pgf_linear_bwd_dw_workspace", B, N, K, n_models)     # > 0 only for a narrow layer at a large batch
+    ws = workspace("linear_dw").get(nbytes, dY.device) if nbytes else None
+    _call(("linear_bwd_dw", B, N, K, n_models), "pgf_linear_bwd_dw_ex", dY.data_ptr(), dY.stride(-2), sdY, X.data_ptr(), X.stride(-2), sX, dW.data_ptr(), sdW,
+           _ptr(db), sdb, B, N, K, int(accumulate), n_models, _ptr(ws), 0 if ws is None else ws.numel() * 4, _stream())
     return dW, db
 
 

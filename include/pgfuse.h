@@ -141,6 +141,13 @@ int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float
 int pgf_linear_bwd_dw(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX,
                       float* dW, long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate,
                       int n_models, void* stream);
+/* The same gradient with caller scratch (pgf_linear_bwd_dw_workspace bytes; 0 = not needed): a narrow layer (N <= 8: the
+ * 768 -> 2 classifier, models.py:81) at a large batch (B >= 512) is computed by batch slabs in parallel, the slab partials
+ * summed in slab order; every other shape takes pgf_linear_bwd_dw's kernel.                                          */
+size_t pgf_linear_bwd_dw_workspace(int B, int N, int K, int n_models);
+int pgf_linear_bwd_dw_ex(const float* dY, long long ldy, long long sdY, const float* X, long long ldx, long long sX,
+                         float* dW, long long sdW, float* db, long long sdb, int B, int N, int K, int accumulate,
+                         int n_models, float* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (a8) fusion MLP, tcgen05 tensor-core path (large batch) ----------------------------------
  * replaces: the same nn.Linear GEMMs when the batch is a real dense contraction.

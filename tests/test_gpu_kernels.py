@@ -213,7 +213,8 @@ def test_minmax_norm_bwd_matches_autograd(dev):
 # ------------------------------------------------------------------------------------------------
 # kernel (b) fp32 CUDA-core path (grouped)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_models,B,N,K", [(1, 8, 2304, 2304), (3, 8, 768, 2304), (2, 5, 2, 768), (1, 19, 260, 512), (48, 8, 768, 768)])
+@pytest.mark.parametrize("n_models,B,N,K", [(1, 8, 2304, 2304), (3, 8, 768, 2304), (2, 5, 2, 768), (1, 19, 260, 512), (48, 8, 768, 768),
+                                            (1, 4099, 2, 768), (2, 1000, 7, 260), (1, 513, 4, 64)])   # narrow layer, large batch: slab dW
 def test_linear_fp32_grouped(dev, n_models, B, N, K):
     from eeg_multimodal_b200 import _lib as L, ops
 
