@@ -241,6 +241,9 @@ int pgf_linear_bwd_dx(const float* dY, long long ldy, long long sdY, const float
   PGF_CHECK_ARG((K % 4) == 0 && (ldx % 4) == 0 && aligned16(W) && aligned16(dX) && (sW % 4) == 0 && (sdX % 4) == 0 &&
                     (!mask_src || ((ld_mask % 4) == 0 && aligned16(mask_src) && (s_mask % 4) == 0)),
                 "pgf_linear_bwd_dx: K, ldx, strides must be multiples of 4 and W, dX, mask 16-byte aligned");
+  if (linear_dx_narrow_applies(B, N))   // a narrow layer at a large batch (the classifier behind the module API): elementwise
+    return linear_bwd_dx_narrow(dY, ldy, sdY, W, sW, mask_src, mask_mode, ld_mask, s_mask, dX, ldx, sdX, B, N, K, n_models,
+                                static_cast<cudaStream_t>(stream));
   if (wide_regime(B, n_models))
     return linear_bwd_dx_wide(dY, ldy, sdY, W, sW, mask_src, mask_mode, ld_mask, s_mask, dX, ldx, sdX, B, N, K, n_models, workspace,
                               workspace_bytes, static_cast<cudaStream_t>(stream));
