@@ -289,6 +289,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                "r"(c1)
                : "memory");
 }
+// the same store with an L2 eviction-priority hint: an output far larger than L2 that the NEXT kernel streams (H1, dZ1:
+// 335 MB) only displaces the operand panels this kernel keeps re-reading if it is written with the normal priority
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1)
@@ -476,6 +483,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     WorkUnit u;
     uint32_t unit = 0, gcount = 0;
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(tempty_bar, 0) : tempty_bar;
+    uint64_t store_policy = 0;
+    if (g.store_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
     while (sched.next(u)) {
       const uint32_t acc = unit & 1, acc_phase = (unit >> 1) & 1;
       const int m0 = (u.tile / nb_n) * TILE_M + static_cast<int>(rank) * BM, n0 = (u.tile % nb_n) * BN;
@@ -612,6 +621,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (leader_thread) {
           if (g.epi == PGF_EPI_ATOMIC_F32) tma_reduce_add_2d(&tmC, sbuf, n, m0);
+          else if (g.store_hint) tma_store_2d_hint(&tmC, sbuf, n, m0, store_policy);
           else tma_store_2d(&tmC, sbuf, n, m0);  // rows >= M / columns >= N are clipped by the tensor map
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -779,6 +789,9 @@ int gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long l
     const long long units = static_cast<long long>(tiles) * best;
     workers = static_cast<int>(units < workers_max ? units : workers_max);
   }
+  // evict_first on plain output stores of tensors far larger than L2 (PGF_GEMM_STORE_HINT=0/1 overrides)
+  static const int hint_env = getenv("PGF_GEMM_STORE_HINT") ? atoi(getenv("PGF_GEMM_STORE_HINT")) : -1;
+  g.store_hint = hint_env >= 0 ? hint_env : 0;
   static const bool one_epi_group = getenv("PGF_GEMM_EPI_GROUPS") != nullptr && getenv("PGF_GEMM_EPI_GROUPS")[0] == '1';
   g.epi_groups = one_epi_group ? 1 : 2;
   cudaLaunchConfig_t cfg = {};
