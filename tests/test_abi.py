@@ -89,3 +89,21 @@ def test_cpu_tensors_are_rejected():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.dp_coeffs(torch.zeros(16), 2.7)
+
+
+def test_gemm_object_is_tcgen05_tma_code():
+    """The large-batch GEMM is tcgen05 / TMEM / TMA code for sm_100a, not a recompiled mma.sync kernel: the SASS of the built
+    object carries UTCHMMA (tcgen05.mma, also in its 2-CTA form), LDTM (tcgen05.ld), UTMALDG / UTMASTG / UTMAREDG (TMA loads,
+    stores, reduce-adds; 2-D and -- for the fp32-parity plane walk -- 3-D) and no HMMA (profiles/sass_gemm_tc.txt)."""
+    import shutil
+    import subprocess
+
+    obj = os.path.join(ROOT, "eeg_multimodal_b200", "build", "gemm_tc.o")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(obj) or not os.path.exists(tool):
+        pytest.skip("gemm_tc.o / cuobjdump not available (the library was not built in this tree)")
+    sass = subprocess.run([tool, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    for needle in ("UTCHMMA.2CTA", "UTCHMMA", "LDTM", "UTMALDG.2D.2CTA", "UTMALDG.3D", "UTMASTG.2D", "UTMAREDG.2D.ADD"):
+        assert needle in sass, needle
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    assert "sm_100a" in subprocess.run([tool, "-lelf", obj], capture_output=True, text=True).stdout
