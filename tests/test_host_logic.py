@@ -324,3 +324,34 @@ def test_single_process_fanout_and_inactive_overlap_hook():
     g = torch.ones(10)
     hook.bucket(g[:4]); hook.bucket(g[4:]); hook.finish(); hook(g)
     assert not hook.active and hook.n_buckets == 2 and torch.equal(g, torch.ones(10))
+
+
+def test_committed_bench_line_keeps_the_driver_contract():
+    """profiles/r2_bench_default.json is the line `python bench.py` printed at HEAD on one B200: every key the driver parses is
+    there, with the roofline / cpu_baseline / e2e objects of the measurement contract and the other BASELINE configurations in
+    config.also."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(__file__))
+    d = json.loads(open(os.path.join(root, "profiles", "r2_bench_default.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "model-samples/sec" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "sweep_synth64k" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(d["value"] - 6 * 65536 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6        # whole-job model-samples/s of the step time
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 65536 * (2560 * 4 + 8) and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    also = d["config"]["also"]
+    assert also["sweep48_b8"]["models_per_gpu"] == 6 and also["sweep48_b8"]["launches_per_step"] == 13.0
+    assert also["dp64k"]["scaling"] == "strong" and also["dp64k"]["n_gpus"] == 1
+    assert 5.0 < also["fp32x3_synth64k"]["fp32_parity_cost"] < 8.0
+    ref = json.loads(open(os.path.join(root, "profiles", "r2_bench_reference_cpu.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"] and ref["gpu_launches"] == 0
+    assert ref["config"]["workload"] == d["config"]["workload"] and ref["config"]["batch_per_model"] == d["config"]["batch_per_model"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
